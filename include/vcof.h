@@ -1,0 +1,96 @@
+/* vcof.h — C ABI of libvcof: the B200-native (sm_100a) kernels behind the VideoCoF
+ * denoising hot path (Wan-2.1 DiT block stack + 3D causal VAE).
+ *
+ * The reference (knightyxp/VideoCoF) has no FFI / operator registry: its boundary is the
+ * Python class API of videox_fun.models / videox_fun.pipeline.  This header
+ * is the layer UNDER that API: one extern "C" entry per kernel family, plain pointers and
+ * sizes only, no torch types.  Each entry cites the reference call site it replaces
+ * (paths relative to the reference repo).  videocof_b200/_lib.py binds it with ctypes; the
+ * reference-side stub a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; tensors are row-major;
+ *     ld* are leading dimensions in ELEMENTS
+ *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered, never
+ *     synchronise and never allocate
+ *   - return 0 on success, negative on error; vcof_last_error() returns the message
+ *     (thread-local).  Nothing here falls back to a CPU path.
+ */
+#ifndef VCOF_H_
+#define VCOF_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VCOF_ABI_VERSION 1
+
+const char* vcof_last_error(void);
+int vcof_abi_version(void);
+
+/* ---- GEMM epilogues -------------------------------------------------------------------- */
+#define VCOF_EPI_BIAS_BF16 0         /* out_bf16 = bf16(acc + bias)                          */
+#define VCOF_EPI_BIAS_GELU_BF16 1    /* out_bf16 = bf16(gelu_tanh(bf16(acc + bias)))         */
+#define VCOF_EPI_BIAS_GATE_RES_F32 2 /* out_f32 += gate[n] * bf16(acc + bias)  (gate NULL=1) */
+#define VCOF_EPI_BIAS_F32 3          /* out_f32  = float(bf16(acc + bias))                   */
+
+/* D[M,N] = A[M,K] (bf16) x W[N,K]^T (bf16, nn.Linear layout) with fused epilogue; tcgen05 +
+ * TMEM + TMA.  Replaces nn.Linear q/k/v/o, ffn.0/ffn.2, text_embedding, head.head and the
+ * patch-embedding Conv3d-as-GEMM: wan_transformer3d.py:264-267, 284-290, 303-304, 457-459,
+ * 543, 662-666, 870; the fused epilogues replace :458 (GELU), :499/:504/:511 (gate+residual). */
+int vcof_gemm_bf16(const void* a, long long lda, const void* w, long long ldw, const void* bias,
+                   const float* gate, void* out, long long ldo, int M, int N, int K, int epilogue,
+                   void* stream);
+
+/* out[Lq, heads*128] = softmax(Q K^T * scale) V per head, non-causal, keys [0, kv_len).
+ * q/k/(v) are [L, heads*128] bf16 (heads interleaved along the row, as .view(b,s,n,d));
+ * with v_transposed != 0, v is V^T stored [heads*128, ldv] (kv contiguous).
+ * Replaces attention()/flash_attention(): attention_utils.py:43-149, 152-210 as called from
+ * wan_transformer3d.py:294-299 (self) and :325-330 (cross, kv_len = 512). */
+int vcof_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                  long long ldv, void* out, long long ldo, int Lq, int Lk, int kv_len, int heads,
+                  int head_dim, float softmax_scale, int v_transposed, void* stream);
+
+/* out_bf16[L,C] = ((LayerNorm(x_f32[L,C], eps) * ln_w + ln_b) * (1 + scale) + shift); every
+ * per-channel vector is fp32 [C] and may be NULL (identity).  Replaces WanLayerNorm + AdaLN
+ * modulate + cast: wan_transformer3d.py:233-243, 495-496, 504 (norm3), 507-508, 547 (head). */
+int vcof_ln_modulate(const float* x, long long ldx, const float* ln_w, const float* ln_b,
+                     const float* shift, const float* scale, void* out, long long ldo, int L, int C,
+                     float eps, void* stream);
+
+/* In place on x_bf16[L,C]: WanRMSNorm over the full row (all heads), then 3-axis RoPE on
+ * interleaved pairs.  y = bf16(bf16(x * bf16(rsqrt(mean(x^2)+eps))) * w); if rope_table != NULL
+ * token (row_offset + l) of the (F,H,W) grid is rotated by table[pos][i] = (cos, sin), i in
+ * [0,64): pairs [0,n_t) use the temporal position tpos[f], [n_t, n_t+n_h) the row, the rest the
+ * column.  Rows whose global token id >= F*H*W are normalised but not rotated.
+ * Replaces wan_transformer3d.py:214-230 (WanRMSNorm) and :135-211 (rope_apply, incl. the
+ * chain-of-frames temporal positions :153-198). */
+int vcof_rmsnorm_rope(void* x, long long ldx, const void* weight, float eps, int L, int C,
+                      int head_dim, const float* rope_table, const int* tpos, int F, int H, int W,
+                      int n_t, int n_h, int row_offset, void* stream);
+
+/* Patchify latents x_bf16[Cin, F, H, W] -> tokens a_bf16[F*(H/2)*(W/2), Cin*4], column order
+ * (c, ph, pw) = the flattened Conv3d weight [C, Cin, 1, 2, 2].  wan_transformer3d.py:870, 879. */
+int vcof_patchify(const void* x, void* a, int Cin, int F, int H, int W, void* stream);
+
+/* Unpatchify head output y_bf16[L, 4*Cout] (column order (ph, pw, c)) -> out_bf16[Cout, F, H, W]
+ * (H, W are the LATENT sizes, L = F*(H/2)*(W/2)).  wan_transformer3d.py:1108-1131. */
+int vcof_unpatchify(const void* y, long long ldy, void* out, int Cout, int F, int H, int W,
+                    void* stream);
+
+/* Small fp32 linear for the timestep path (runs under autocast(fp32) in the reference):
+ * out_f32[B,N] = act_out( act_in(x_f32[B,K]) @ W_bf16[N,K]^T + bias_bf16[N] ), act: 0 none, 1 SiLU.
+ * wan_transformer3d.py:668-670, 913-929. */
+int vcof_linear_f32(const float* x, const void* w, const void* bias, float* out, int B, int N, int K,
+                    int act_in, int act_out, void* stream);
+
+/* ---- diagnostics ---------------------------------------------------------------------- */
+/* One 128x128x64 tcgen05 tile with hand-swizzled operands (no TMA): d_f32[128,128] =
+ * a_bf16[128,64] x b_bf16[128,64]^T.  mode bit0: B staged MN-major; bit1: A fed from TMEM.
+ * Pins the descriptor conventions the GEMM / attention kernels depend on. */
+int vcof_debug_umma_probe(const void* a, const void* b, float* d, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCOF_H_ */

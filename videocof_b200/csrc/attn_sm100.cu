@@ -1,0 +1,418 @@
+// attn_sm100.cu — FlashAttention-style non-causal attention forward on tcgen05
+// for sm_100a, head_dim 128, bf16 in / bf16 out, fp32 softmax statistics.
+//
+// Replaces the reference's attention() dispatch (videox_fun/models/attention_utils.py:152-210,
+// i.e. flash_attn_varlen_func / SDPA) for the DiT self-attention
+// (wan_transformer3d.py:294-299) and text cross-attention (:325-330).
+//
+// One persistent CTA per SM walks (head, 256-query-row block) work items.  Each
+// item keeps TWO 128-row Q tiles in flight (ping-pong) so that the tensor pipe
+// works on one tile while the softmax warps work on the other:
+//
+//   TMEM (512 columns): S0 | S1 | O0 | O1   (128 fp32 columns each);
+//   P_t (bf16, 64 columns) aliases the start of S_t and feeds the PV MMA
+//   directly from TMEM (tcgen05.mma with A in tensor memory).
+//
+//   warps 0-3  : softmax + epilogue for tile 0 (thread i <-> TMEM lane i <-> one query row)
+//   warps 4-7  : softmax + epilogue for tile 1
+//   warp  8    : TMA producer (Q tiles, K/V ring, 128B-swizzled 64-column boxes)
+//   warp  9    : tcgen05.mma issuer: S_t = Q_t K_j^T, then O_t += P_t V_j
+//   warp  10   : TMEM allocator
+//
+// Online softmax uses exp2 with the scale folded in, and a lazy rescale: the
+// running row max is only advanced (and O_t rescaled in TMEM) when it grew by
+// more than 2^8, so in steady state the softmax warps never touch O.
+#include "vcof_common.cuh"
+#include "../../include/vcof.h"
+
+namespace vcof {
+
+constexpr int kHD = 128;              // head dim
+constexpr int kQT = 128;              // query rows per tile
+constexpr int kKT = 128;              // kv rows per tile
+constexpr int kTile = kQT * kHD * 2;  // 32 KiB bf16 tile
+constexpr int kHalf = kTile / 2;      // one 64-column TMA box
+constexpr int kKVStages = 2;
+constexpr int kAttnThreads = 384;
+constexpr float kRescaleThresh = 8.0f;  // log2 units
+
+struct AttnArgs {
+  int Lq, kv_len, heads, num_q_blocks;
+  float scale_log2;
+  bf16* out;
+  long long ldo;
+};
+
+constexpr int kAttnSmem = 2 * kTile + 2 * kKVStages * kTile + 256 + 1024;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool V_TRANS>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* sQ = smem;                          // 2 tiles
+  uint8_t* sK = smem + 2 * kTile;              // kKVStages tiles
+  uint8_t* sV = sK + kKVStages * kTile;        // kKVStages tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKVStages * kTile);
+  const uint32_t b0 = smem_u32(bars);
+  // barrier map (8 bytes each)
+  const uint32_t q_full = b0, q_empty = b0 + 16;
+  const uint32_t k_full = b0 + 32, k_empty = b0 + 48;
+  const uint32_t v_full = b0 + 64, v_empty = b0 + 80;
+  const uint32_t s_full = b0 + 96, p_full = b0 + 112, o_full = b0 + 128;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 9 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full + 8 * i, 1);
+      mbar_init(q_empty + 8 * i, 1);
+      mbar_init(k_full + 8 * i, 1);
+      mbar_init(k_empty + 8 * i, 1);
+      mbar_init(v_full + 8 * i, 1);
+      mbar_init(v_empty + 8 * i, 1);
+      mbar_init(s_full + 8 * i, 1);
+      mbar_init(p_full + 8 * i, 4);
+      mbar_init(o_full + 8 * i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 10) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_kv = (p.kv_len + kKT - 1) / kKT;
+  const int num_items = p.heads * p.num_q_blocks;
+
+  if (warp == 8) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t item_ph = 0;
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, item_ph ^= 1) {
+        const int head = item / p.num_q_blocks;
+        const int q0 = (item % p.num_q_blocks) * 2 * kQT;
+        const int col = head * kHD;
+        auto load_q = [&](int t) {
+          mbar_wait(q_empty + 8 * t, item_ph ^ 1);
+          mbar_expect_tx(q_full + 8 * t, kTile);
+          tma_load_2d(smem_u32(sQ + t * kTile), &tmQ, q_full + 8 * t, col, q0 + t * kQT);
+          tma_load_2d(smem_u32(sQ + t * kTile + kHalf), &tmQ, q_full + 8 * t, col + 64,
+                      q0 + t * kQT);
+        };
+        auto load_k = [&](int j) {
+          mbar_wait(k_empty + 8 * ks, kph ^ 1);
+          mbar_expect_tx(k_full + 8 * ks, kTile);
+          tma_load_2d(smem_u32(sK + ks * kTile), &tmK, k_full + 8 * ks, col, j * kKT);
+          tma_load_2d(smem_u32(sK + ks * kTile + kHalf), &tmK, k_full + 8 * ks, col + 64, j * kKT);
+          if (++ks == kKVStages) { ks = 0; kph ^= 1; }
+        };
+        auto load_v = [&](int j) {
+          mbar_wait(v_empty + 8 * vs, vph ^ 1);
+          mbar_expect_tx(v_full + 8 * vs, kTile);
+          if (V_TRANS) {
+            // V^T [C, Lk]: box = 64 kv columns x 128 head-dim rows
+            tma_load_2d(smem_u32(sV + vs * kTile), &tmV, v_full + 8 * vs, j * kKT, col);
+            tma_load_2d(smem_u32(sV + vs * kTile + kHalf), &tmV, v_full + 8 * vs, j * kKT + 64,
+                        col);
+          } else {
+            tma_load_2d(smem_u32(sV + vs * kTile), &tmV, v_full + 8 * vs, col, j * kKT);
+            tma_load_2d(smem_u32(sV + vs * kTile + kHalf), &tmV, v_full + 8 * vs, col + 64,
+                        j * kKT);
+          }
+          if (++vs == kKVStages) { vs = 0; vph ^= 1; }
+        };
+        load_q(0);
+        load_k(0);
+        load_q(1);
+        load_v(0);
+        for (int j = 1; j < n_kv; ++j) {
+          load_k(j);
+          load_v(j);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kKT, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kQT, kHD, false, !V_TRANS);
+      uint32_t item_ph = 0;
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0;
+      uint32_t pph[2] = {0, 0};
+      const uint32_t tS[2] = {tmem_base, tmem_base + 128};
+      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+
+      auto mma_s = [&](int t, int kstage) {
+        const uint32_t a = smem_u32(sQ + t * kTile);
+        const uint32_t b = smem_u32(sK + kstage * kTile);
+#pragma unroll
+        for (int k = 0; k < kHD / 16; ++k) {
+          const uint32_t off = (k >> 2) * kHalf + (k & 3) * 32;
+          umma_ss(tS[t], make_desc_kmajor_sw128(a + off), make_desc_kmajor_sw128(b + off),
+                  idesc_qk, k != 0);
+        }
+      };
+      auto mma_pv = [&](int t, int vstage, bool first) {
+        const uint32_t b = smem_u32(sV + vstage * kTile);
+#pragma unroll
+        for (int k = 0; k < kKT / 16; ++k) {
+          uint64_t bd;
+          if (V_TRANS) {
+            bd = make_desc_kmajor_sw128(b + (k >> 2) * kHalf + (k & 3) * 32);
+          } else {
+            bd = make_desc_mnmajor_sw128(b + k * 16 * 128, kHalf, 1024);
+          }
+          umma_ts(tO[t], tS[t] + k * 8, bd, idesc_pv, (!first || k != 0));
+        }
+      };
+
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, item_ph ^= 1) {
+        // prologue: S0(0), S1(0)
+        mbar_wait(q_full + 0, item_ph);
+        mbar_wait(k_full + 8 * ks, kph);
+        tc_fence_after();
+        mma_s(0, ks);
+        umma_commit(s_full + 0);
+        if (n_kv == 1) umma_commit(q_empty + 0);
+        mbar_wait(q_full + 8, item_ph);
+        tc_fence_after();
+        mma_s(1, ks);
+        umma_commit(s_full + 8);
+        if (n_kv == 1) umma_commit(q_empty + 8);
+        umma_commit(k_empty + 8 * ks);
+        if (++ks == kKVStages) { ks = 0; kph ^= 1; }
+
+        for (int j = 0; j < n_kv; ++j) {
+          const bool last = (j + 1 == n_kv);
+          // ---- tile 0: O0 += P0(j) V_j ; then S0(j+1)
+          mbar_wait(v_full + 8 * vs, vph);
+          mbar_wait(p_full + 0, pph[0]);
+          pph[0] ^= 1;
+          tc_fence_after();
+          mma_pv(0, vs, j == 0);
+          if (!last) {
+            mbar_wait(k_full + 8 * ks, kph);
+            tc_fence_after();
+            mma_s(0, ks);
+            umma_commit(s_full + 0);
+            if (j + 2 == n_kv) umma_commit(q_empty + 0);
+          } else {
+            umma_commit(o_full + 0);
+          }
+          // ---- tile 1: O1 += P1(j) V_j ; then S1(j+1)
+          mbar_wait(p_full + 8, pph[1]);
+          pph[1] ^= 1;
+          tc_fence_after();
+          mma_pv(1, vs, j == 0);
+          umma_commit(v_empty + 8 * vs);
+          if (++vs == kKVStages) { vs = 0; vph ^= 1; }
+          if (!last) {
+            mma_s(1, ks);
+            umma_commit(s_full + 8);
+            if (j + 2 == n_kv) umma_commit(q_empty + 8);
+            umma_commit(k_empty + 8 * ks);
+            if (++ks == kKVStages) { ks = 0; kph ^= 1; }
+          } else {
+            umma_commit(o_full + 8);
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // =========================== softmax + epilogue ===========================
+    const int t = warp >> 2;                         // which Q tile
+    const uint32_t lane_base = ((warp & 3) * 32u) << 16;
+    const uint32_t tS = tmem_base + t * 128 + lane_base;
+    const uint32_t tO = tmem_base + 256 + t * 128 + lane_base;
+    const int row_in_tile = (warp & 3) * 32 + lane;
+    uint32_t sph = 0, oph = 0;
+    const int rem = p.kv_len - (n_kv - 1) * kKT;  // valid columns in the last kv tile (1..128)
+
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int head = item / p.num_q_blocks;
+      const int q0 = (item % p.num_q_blocks) * 2 * kQT;
+      float m_ref = -INFINITY;  // running (possibly stale) row max, raw score units
+      float l = 0.f;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(s_full + 8 * t, sph);
+        sph ^= 1;
+        tc_fence_after();
+        uint32_t s[128];
+        tmem_ld32(tS + 0, s + 0);
+        tmem_ld32(tS + 32, s + 32);
+        tmem_ld32(tS + 64, s + 64);
+        tmem_ld32(tS + 96, s + 96);
+        tmem_ld_wait();
+        if (j == n_kv - 1 && rem < kKT) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (c >= rem) s[c] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 128; c += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[c]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+        }
+        const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        const float m_new = fmaxf(m_ref, m_tile);
+        const bool grow = (m_new - m_ref) * p.scale_log2 > kRescaleThresh;  // true at j == 0
+        if (__any_sync(0xffffffffu, grow)) {
+          if (j > 0) {
+            // PV_t(j-1) retired before s_full fired (same commit group), and PV_t(j)
+            // is not issued until we arrive on p_full: O_t is ours to rescale.
+            const float alpha = ex2((m_ref - m_new) * p.scale_log2);
+            l *= alpha;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st32(tO + c * 32, o);
+            }
+            tmem_st_wait();
+          }
+          m_ref = m_new;
+        }
+        const float mb = m_ref * p.scale_log2;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const int cc = h * 64 + c * 2;
+            const float p0 = ex2(fmaf(__uint_as_float(s[cc + 0]), p.scale_log2, -mb));
+            const float p1 = ex2(fmaf(__uint_as_float(s[cc + 1]), p.scale_log2, -mb));
+            const float p2 = ex2(fmaf(__uint_as_float(s[cc + 2]), p.scale_log2, -mb));
+            const float p3 = ex2(fmaf(__uint_as_float(s[cc + 3]), p.scale_log2, -mb));
+            l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+            pk[c] = pack_bf16x2(p0, p1);
+            pk[c + 1] = pack_bf16x2(p2, p3);
+          }
+          tmem_st32(tS + h * 32, pk);
+        }
+        l += (l0 + l1) + (l2 + l3);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full + 8 * t);
+      }
+      // ---- epilogue: O_t / l -> bf16 -> global
+      mbar_wait(o_full + 8 * t, oph);
+      oph ^= 1;
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      const int row = q0 + t * kQT + row_in_tile;
+      bf16* orow = p.out + (long long)row * p.ldo + head * kHD;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tmem_ld_wait();
+        if (row < p.Lq) {
+          uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+            o4[q] = w;
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace vcof
+
+using namespace vcof;
+
+extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long long ldk,
+                             const void* v, long long ldv, void* out, long long ldo, int Lq, int Lk,
+                             int kv_len, int heads, int head_dim, float softmax_scale,
+                             int v_transposed, void* stream) {
+  VCOF_REQUIRE(head_dim == kHD, "vcof_attn_fwd: head_dim %d unsupported (only 128)", head_dim);
+  VCOF_REQUIRE(Lq > 0 && Lk > 0 && heads > 0, "vcof_attn_fwd: empty problem");
+  VCOF_REQUIRE(kv_len >= 1 && kv_len <= Lk, "vcof_attn_fwd: kv_len %d outside [1, %d]", kv_len, Lk);
+  VCOF_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
+               "vcof_attn_fwd: leading dims must be multiples of 8 elements");
+  VCOF_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "vcof_attn_fwd: out not 16B aligned");
+  const int C = heads * kHD;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc = make_tmap_2d_bf16(&tmQ, q, (uint64_t)C, (uint64_t)Lq, (uint64_t)ldq * 2, 64, kQT);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmK, k, (uint64_t)C, (uint64_t)kv_len, (uint64_t)ldk * 2, 64, kKT);
+  if (rc) return rc;
+  if (v_transposed) {
+    // V^T stored [C, ldv] with kv contiguous
+    rc = make_tmap_2d_bf16(&tmV, v, (uint64_t)kv_len, (uint64_t)C, (uint64_t)ldv * 2, 64, kHD);
+  } else {
+    rc = make_tmap_2d_bf16(&tmV, v, (uint64_t)C, (uint64_t)kv_len, (uint64_t)ldv * 2, 64, kKT);
+  }
+  if (rc) return rc;
+  AttnArgs a;
+  a.Lq = Lq;
+  a.kv_len = kv_len;
+  a.heads = heads;
+  a.num_q_blocks = (Lq + 2 * kQT - 1) / (2 * kQT);
+  a.scale_log2 = softmax_scale * 1.4426950408889634f;
+  a.out = reinterpret_cast<bf16*>(out);
+  a.ldo = ldo;
+  const int items = a.heads * a.num_q_blocks;
+  const int grid = items < sm_count() ? items : sm_count();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static bool attr_set[2] = {false, false};
+  if (v_transposed) {
+    if (!attr_set[1]) {
+      VCOF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+      attr_set[1] = true;
+    }
+    attn_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, a);
+  } else {
+    if (!attr_set[0]) {
+      VCOF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+      attr_set[0] = true;
+    }
+    attn_fwd_kernel<false><<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, a);
+  }
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,350 @@
+// gemm_sm100.cu — persistent, warp-specialised bf16 GEMM on tcgen05 for sm_100a.
+//
+//   D[M,N] = A[M,K] * W[N,K]^T  (+ bias[N]) with a fused epilogue
+//
+// A is an activation matrix (tokens x channels, row-major) and W an nn.Linear
+// weight (out x in, row-major), so both operands are K-major: the canonical
+// tcgen05 case.  One CTA per SM loops over 128 x BN output tiles:
+//   warp 4   : TMA producer  (A tile 128x64, W tile BNx64, 128B swizzle, mbarrier ring)
+//   warp 5   : tcgen05.mma issuer (one elected lane), fp32 accumulators in TMEM,
+//              double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 0-3: epilogue (tcgen05.ld 32x32b -> registers -> fused op -> global)
+//
+// Replaces the cuBLAS calls behind every nn.Linear on the DiT path
+// (reference videox_fun/models/wan_transformer3d.py:264-267, 457-459, 543) and fuses
+// what the reference runs as separate ATen kernels afterwards: bias, GELU(tanh)
+// (:458), the AdaLN gate and fp32 residual accumulate (:499, :504, :511).
+#include "vcof_common.cuh"
+#include "../../include/vcof.h"
+
+namespace vcof {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 192;
+
+struct GemmArgs {
+  int M, N, K;
+  const bf16* bias;   // [N] or nullptr
+  const float* gate;  // [N] fp32 or nullptr (EPI 2)
+  void* out;          // bf16 or fp32 [M, ldo]
+  long long ldo;
+  int group_m;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +align slack
+  static constexpr int kTmemCols = 2 * BN;
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk,
+                                            int& n_blk) {
+  int per_group = group_m * num_n;
+  int g = tile / per_group;
+  int first_m = g * group_m;
+  int gsz = min(group_m, num_m - first_m);
+  int r = tile - g * per_group;
+  m_blk = first_m + r % gsz;
+  n_blk = r / gsz;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 GemmArgs p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + S * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  // bars: full[S], empty[S], tfull[2], tempty[2], then tmem base slot
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * S;
+  const uint32_t bar_tfull = bar_empty + 8 * S;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 5) {
+    if (lane == 0) {
+      for (int i = 0; i < S; ++i) {
+        mbar_init(bar_full + 8 * i, 1);
+        mbar_init(bar_empty + 8 * i, 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_tfull + 8 * i, 1);
+        mbar_init(bar_tempty + 8 * i, 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + kBM - 1) / kBM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+
+  if (warp == 4) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_expect_tx(bar_full + 8 * s, Cfg::kStageBytes);
+          tma_load_2d(smem_u32(sA + s * Cfg::kABytes), &tmA, bar_full + 8 * s, kb * kBK,
+                      m_blk * kBM);
+          tma_load_2d(smem_u32(sB + s * Cfg::kBBytes), &tmB, bar_full + 8 * s, kb * kBK,
+                      n_blk * BN);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, false, false);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * Cfg::kABytes);
+          const uint32_t b_base = smem_u32(sB + s * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            umma_ss(d_tmem, make_desc_kmajor_sw128(a_base + k * 32),
+                    make_desc_kmajor_sw128(b_base + k * 32), idesc, (kb | k) != 0);
+          }
+          umma_commit(bar_empty + 8 * s);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps 0..3 ----------------
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int m_blk, n_blk;
+      tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * acc, acc_ph);
+      tc_fence_after();
+      const int row = m_blk * kBM + warp * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + ((warp * 32u) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full_chunk = (n0 + 32 <= p.N);
+        if (p.bias != nullptr) {
+          if (full_chunk) {
+            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 b = __ldg(bp + q);
+              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __bfloat1622float2(b2[e]);
+                v[q * 8 + e * 2] += f.x;
+                v[q * 8 + e * 2 + 1] += f.y;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) v[j] += __bfloat162float(p.bias[n0 + j]);
+          }
+        }
+        if (EPI == VCOF_EPI_BIAS_GELU_BF16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(bf16_round(v[j]));
+        }
+        if (!row_ok) continue;
+        if (EPI == VCOF_EPI_BIAS_BF16 || EPI == VCOF_EPI_BIAS_GELU_BF16) {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + n0;
+          if (full_chunk) {
+            uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 w;
+              w.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+              w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+              w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+              w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              o4[q] = w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else if (EPI == VCOF_EPI_BIAS_GATE_RES_F32) {
+          // x[row, n] += gate[n] * bf16(acc + bias)   (reference :499 / :504 / :511:
+          // the Linear output is a bf16 tensor, the residual stream is fp32)
+          float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0;
+          if (full_chunk) {
+            float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 x = o4[q];
+              float g0 = 1.f, g1 = 1.f, g2 = 1.f, g3 = 1.f;
+              if (p.gate != nullptr) {
+                float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + n0) + q);
+                g0 = g.x; g1 = g.y; g2 = g.z; g3 = g.w;
+              }
+              x.x += g0 * bf16_round(v[q * 4 + 0]);
+              x.y += g1 * bf16_round(v[q * 4 + 1]);
+              x.z += g2 * bf16_round(v[q * 4 + 2]);
+              x.w += g3 * bf16_round(v[q * 4 + 3]);
+              o4[q] = x;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) {
+                float g = p.gate ? p.gate[n0 + j] : 1.f;
+                o[j] += g * bf16_round(v[j]);
+              }
+          }
+        } else {  // VCOF_EPI_BIAS_F32: out = float(bf16(acc + bias))
+          float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0;
+          if (full_chunk) {
+            float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              o4[q] = make_float4(bf16_round(v[q * 4]), bf16_round(v[q * 4 + 1]),
+                                  bf16_round(v[q * 4 + 2]), bf16_round(v[q * 4 + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) o[j] = bf16_round(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_bf16_kernel<BN, EPI>;
+  if (!attr_set) {
+    VCOF_CHECK_CUDA(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int num_m = (args.M + kBM - 1) / kBM;
+  const int num_n = (args.N + BN - 1) / BN;
+  const int tiles = num_m * num_n;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, args);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                        const GemmArgs& args, cudaStream_t stream) {
+  switch (epi) {
+    case VCOF_EPI_BIAS_BF16: return launch_gemm<BN, VCOF_EPI_BIAS_BF16>(tmA, tmB, args, stream);
+    case VCOF_EPI_BIAS_GELU_BF16:
+      return launch_gemm<BN, VCOF_EPI_BIAS_GELU_BF16>(tmA, tmB, args, stream);
+    case VCOF_EPI_BIAS_GATE_RES_F32:
+      return launch_gemm<BN, VCOF_EPI_BIAS_GATE_RES_F32>(tmA, tmB, args, stream);
+    case VCOF_EPI_BIAS_F32: return launch_gemm<BN, VCOF_EPI_BIAS_F32>(tmA, tmB, args, stream);
+  }
+  set_last_error("vcof_gemm_bf16: unknown epilogue %d", epi);
+  return -1;
+}
+
+}  // namespace vcof
+
+using namespace vcof;
+
+extern "C" int vcof_gemm_bf16(const void* a, long long lda, const void* w, long long ldw,
+                              const void* bias, const float* gate, void* out, long long ldo, int M,
+                              int N, int K, int epilogue, void* stream) {
+  VCOF_REQUIRE(M > 0 && N > 0 && K > 0, "vcof_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  VCOF_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0,
+               "vcof_gemm_bf16: K/lda/ldw must be multiples of 8 (16-byte TMA rows)");
+  const bool f32_out = (epilogue == VCOF_EPI_BIAS_GATE_RES_F32 || epilogue == VCOF_EPI_BIAS_F32);
+  VCOF_REQUIRE(ldo % (f32_out ? 4 : 8) == 0, "vcof_gemm_bf16: ldo=%lld breaks 16-byte row alignment",
+               ldo);
+  VCOF_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "vcof_gemm_bf16: out not 16B aligned");
+  VCOF_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+               "vcof_gemm_bf16: bias not 16B aligned");
+  VCOF_REQUIRE(gate == nullptr || (reinterpret_cast<uintptr_t>(gate) & 15) == 0,
+               "vcof_gemm_bf16: gate not 16B aligned");
+  const int BN = (N > 128) ? 256 : (N > 64 ? 128 : 64);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d_bf16(&tmA, a, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kBM);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, w, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, kBK, BN);
+  if (rc) return rc;
+  GemmArgs args;
+  args.M = M; args.N = N; args.K = K;
+  args.bias = reinterpret_cast<const bf16*>(bias);
+  args.gate = gate;
+  args.out = out;
+  args.ldo = ldo;
+  args.group_m = 8;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (BN == 256) return dispatch_epi<256>(epilogue, tmA, tmB, args, st);
+  if (BN == 128) return dispatch_epi<128>(epilogue, tmA, tmB, args, st);
+  return dispatch_epi<64>(epilogue, tmA, tmB, args, st);
+}

@@ -1,0 +1,191 @@
+"""Tensor-level wrappers over the C ABI (include/vcof.h).
+
+PyTorch is used for device memory and streams only: every function here checks its
+arguments, allocates the output with torch, and launches exactly one libvcof kernel on
+the current CUDA stream.  No function has a PyTorch/CPU fallback — a CPU tensor or a
+missing libvcof.so raises.
+"""
+import math
+
+import torch
+
+from . import _lib
+
+EPI = {"bias": 0, "bias_gelu": 1, "bias_gate_res": 2, "bias_f32": 3}
+
+# kernel launches since the last reset (bench.py reports it as gpu_launches)
+_launches = 0
+
+
+def launches():
+    return _launches
+
+
+def reset_launches():
+    global _launches
+    _launches = 0
+
+
+def _call(name, *args):
+    global _launches
+    _launches += 1
+    _lib.call(name, *args)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name, dims=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.VcofError(f"{name}: expected a CUDA tensor (libvcof has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.VcofError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if dims is not None and t.dim() != dims:
+        raise _lib.VcofError(f"{name}: expected {dims} dims, got shape {tuple(t.shape)}")
+    if t.dim() >= 1 and t.stride(-1) != 1:
+        raise _lib.VcofError(f"{name}: innermost dimension must be contiguous")
+    return t
+
+
+def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
+    """out = epilogue(a @ w.T + bias).  a [M,K] bf16, w [N,K] bf16 (nn.Linear layout).
+
+    epilogue: "bias" -> bf16 [M,N]; "bias_gelu" -> bf16 gelu_tanh; "bias_f32" -> fp32 (value
+    rounded through bf16); "bias_gate_res" -> `out` (fp32 [M,N], required) += gate * bf16(.)
+    """
+    _chk(a, torch.bfloat16, "gemm.a", 2)
+    _chk(w, torch.bfloat16, "gemm.w", 2)
+    M, K = a.shape
+    N, K2 = w.shape
+    if K != K2:
+        raise _lib.VcofError(f"gemm: K mismatch {K} vs {K2}")
+    epi = EPI[epilogue]
+    if bias is not None:
+        _chk(bias, torch.bfloat16, "gemm.bias", 1)
+    if gate is not None:
+        _chk(gate, torch.float32, "gemm.gate", 1)
+    if epi == 2:
+        if out is None:
+            raise _lib.VcofError("gemm: bias_gate_res needs the fp32 residual in `out`")
+        _chk(out, torch.float32, "gemm.out", 2)
+    elif epi == 3:
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+        _chk(out, torch.float32, "gemm.out", 2)
+    else:
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+        _chk(out, torch.bfloat16, "gemm.out", 2)
+    if tuple(out.shape) != (M, N):
+        raise _lib.VcofError(f"gemm: out shape {tuple(out.shape)} != {(M, N)}")
+    _call("vcof_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _p(bias),
+          _p(gate), out.data_ptr(), out.stride(0), M, N, K, epi, _stream())
+    return out
+
+
+def attention(q, k, v, heads, kv_len=None, scale=None, out=None, v_transposed=False):
+    """softmax(q k^T * scale) v per head.  q [Lq, heads*128], k [Lk, heads*128],
+    v [Lk, heads*128] (or v^T [heads*128, Lk'] when v_transposed); bf16."""
+    _chk(q, torch.bfloat16, "attention.q", 2)
+    _chk(k, torch.bfloat16, "attention.k", 2)
+    _chk(v, torch.bfloat16, "attention.v", 2)
+    Lq, C = q.shape
+    Lk = k.shape[0]
+    hd = C // heads
+    if kv_len is None:
+        kv_len = Lk
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    if out is None:
+        out = torch.empty((Lq, C), dtype=torch.bfloat16, device=q.device)
+    _chk(out, torch.bfloat16, "attention.out", 2)
+    _call("vcof_attn_fwd", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+          v.stride(0), out.data_ptr(), out.stride(0), Lq, Lk, kv_len, heads, hd, float(scale),
+          1 if v_transposed else 0, _stream())
+    return out
+
+
+def ln_modulate(x, ln_w=None, ln_b=None, shift=None, scale=None, eps=1e-6, out=None):
+    """bf16((LayerNorm(x) * ln_w + ln_b) * (1 + scale) + shift); x fp32 [L,C], vectors fp32 [C]."""
+    _chk(x, torch.float32, "ln_modulate.x", 2)
+    L, C = x.shape
+    for n, t in (("ln_w", ln_w), ("ln_b", ln_b), ("shift", shift), ("scale", scale)):
+        if t is not None:
+            _chk(t, torch.float32, "ln_modulate." + n)
+            if t.numel() != C or not t.is_contiguous():
+                raise _lib.VcofError(f"ln_modulate.{n}: need a contiguous [{C}] vector")
+    if out is None:
+        out = torch.empty((L, C), dtype=torch.bfloat16, device=x.device)
+    _chk(out, torch.bfloat16, "ln_modulate.out", 2)
+    _call("vcof_ln_modulate", x.data_ptr(), x.stride(0), _p(ln_w), _p(ln_b), _p(shift), _p(scale),
+          out.data_ptr(), out.stride(0), L, C, float(eps), _stream())
+    return out
+
+
+class RopeSpec:
+    """Device-side description of the 3-axis rotary embedding for one sample.
+
+    table: fp32 [1024, head_dim/2, 2] (cos, sin) built from the model's complex128 `freqs`;
+    tpos : int32 [F] temporal position per latent frame (plain / paired / chain-of-frames);
+    (F,H,W): patch grid; n_t/n_h: number of complex pairs on the temporal / height axes.
+    """
+
+    def __init__(self, table, tpos, F, H, W, n_t, n_h, row_offset=0):
+        self.table, self.tpos = table, tpos
+        self.F, self.H, self.W, self.n_t, self.n_h, self.row_offset = F, H, W, n_t, n_h, row_offset
+
+
+def rmsnorm_rope_(x, weight, eps, head_dim, rope=None):
+    """In place: WanRMSNorm over the full row, then (optionally) RoPE.  x bf16 [L,C]."""
+    _chk(x, torch.bfloat16, "rmsnorm_rope.x", 2)
+    _chk(weight, torch.bfloat16, "rmsnorm_rope.weight", 1)
+    L, C = x.shape
+    if rope is None:
+        _call("vcof_rmsnorm_rope", x.data_ptr(), x.stride(0), weight.data_ptr(), float(eps), L, C,
+              head_dim, None, None, 1, 1, 1, 0, 0, 0, _stream())
+    else:
+        _chk(rope.table, torch.float32, "rope.table")
+        _chk(rope.tpos, torch.int32, "rope.tpos")
+        _call("vcof_rmsnorm_rope", x.data_ptr(), x.stride(0), weight.data_ptr(), float(eps), L, C,
+              head_dim, rope.table.data_ptr(), rope.tpos.data_ptr(), rope.F, rope.H, rope.W,
+              rope.n_t, rope.n_h, rope.row_offset, _stream())
+    return x
+
+
+def patchify(x):
+    """x bf16 [Cin,F,H,W] -> [F*(H/2)*(W/2), Cin*4] (column order c, ph, pw)."""
+    _chk(x, torch.bfloat16, "patchify.x", 4)
+    if not x.is_contiguous():
+        raise _lib.VcofError("patchify.x must be contiguous")
+    Cin, F, H, W = x.shape
+    a = torch.empty((F * (H // 2) * (W // 2), Cin * 4), dtype=torch.bfloat16, device=x.device)
+    _call("vcof_patchify", x.data_ptr(), a.data_ptr(), Cin, F, H, W, _stream())
+    return a
+
+
+def unpatchify(y, Cout, F, H, W, out=None):
+    """y bf16 [L, 4*Cout] (column order ph, pw, c) -> [Cout, F, H, W] (latent sizes)."""
+    _chk(y, torch.bfloat16, "unpatchify.y", 2)
+    if out is None:
+        out = torch.empty((Cout, F, H, W), dtype=torch.bfloat16, device=y.device)
+    _call("vcof_unpatchify", y.data_ptr(), y.stride(0), out.data_ptr(), Cout, F, H, W, _stream())
+    return out
+
+
+def linear_f32(x, w, bias=None, act_in=False, act_out=False):
+    """fp32 act_out(act_in(x) @ w.T + bias) with bf16 weights; act = SiLU.  x fp32 [B,K]."""
+    _chk(x, torch.float32, "linear_f32.x", 2)
+    _chk(w, torch.bfloat16, "linear_f32.w", 2)
+    if not x.is_contiguous() or not w.is_contiguous():
+        raise _lib.VcofError("linear_f32: x and w must be contiguous")
+    B, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((B, N), dtype=torch.float32, device=x.device)
+    _call("vcof_linear_f32", x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, N, K,
+          int(act_in), int(act_out), _stream())
+    return out
