@@ -1,0 +1,55 @@
+"""The CPU oracle against golden outputs of the UNMODIFIED reference (tools/gen_golden.py).
+
+These fixtures are what pins oracle/: the reference ships no tests or golden vectors of its own
+(SURVEY.md §4), so the goldens were produced by executing its files in the build container.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gen_golden import DIT_CASES, ROPE_MODES, checksum, dit_inputs
+from oracle.dit_oracle import DiTConfig, dit_forward, make_dit_params, temporal_positions
+
+
+@pytest.mark.parametrize("name", list(DIT_CASES))
+def test_dit_oracle_matches_reference_golden(name, golden_dir):
+    ckw, shape, n_ctx, B = DIT_CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = DiTConfig(**ckw)
+    params = make_dit_params(cfg, seed=11)
+    assert checksum(params) == pytest.approx(float(gold["param_checksum"]), rel=1e-12), \
+        "parameter generator drifted from the one the golden was made with"
+    x, ctx, t = dit_inputs(shape, n_ctx, cfg.text_dim, B, seed=23)
+    f = shape[1]
+    seq_len = f * (shape[2] // 2) * (shape[3] // 2)
+    for mode, mk in ROPE_MODES.items():
+        key = "out_" + mode
+        if key not in gold.files:
+            continue
+        y = dit_forward(params, cfg, x, t, ctx, seq_len, **mk(f, B))
+        ref = torch.from_numpy(gold[key])
+        err = float((y - ref).abs().max())
+        assert err < 2e-5 * max(1.0, float(ref.abs().max())), (name, mode, err)
+
+
+def test_temporal_positions_modes():
+    # wan_transformer3d.py:153-191: plain / paired / chain-of-frames
+    assert temporal_positions(5) == [0, 1, 2, 3, 4]
+    assert temporal_positions(5, 2) == [0, 1, 0, 1, 2]
+    assert temporal_positions(5, 2, (2, 3)) == [1, 2, 0, 1, 2]
+    assert temporal_positions(21, 10, (10, 11)) == list(range(1, 11)) + [0] + list(range(1, 11))
+
+
+def test_bf16_emulation_close_to_fp32_gold():
+    ckw, shape, n_ctx, B = DIT_CASES["dit_tiny"]
+    cfg = DiTConfig(**ckw)
+    params = make_dit_params(cfg, seed=11)
+    x, ctx, t = dit_inputs(shape, n_ctx, cfg.text_dim, B, seed=23)
+    seq_len = shape[1] * (shape[2] // 2) * (shape[3] // 2)
+    a = dit_forward(params, cfg, x, t, ctx, seq_len)
+    b = dit_forward(params, cfg, x.bfloat16().float(), t, [c.bfloat16().float() for c in ctx], seq_len,
+                    emulate_bf16=True)
+    rel = float((a - b).norm() / a.norm())
+    assert rel < 3e-2, rel

@@ -1,0 +1,146 @@
+"""Load the UNMODIFIED reference hot-path files from /root/reference for golden generation.
+
+The reference package cannot be imported as a whole here (diffusers, accelerate, omegaconf …
+are not installed and there is no network).  Its hot-path files import only a
+handful of diffusers names, so this module installs tiny in-memory stand-ins for those names
+and loads the files with importlib straight from the read-only mount.  Nothing is copied.
+
+Used only by tools/gen_golden.py in the build container; /root/reference does not exist on
+the GPU box, so nothing under tests/, bench.py or the product imports this at run time.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+REF = os.environ.get("VCOF_REFERENCE", "/root/reference")
+
+
+class _Config(dict):
+    __getattr__ = dict.get
+
+
+def _register_to_config(init):
+    import functools
+    import inspect
+
+    @functools.wraps(init)
+    def wrapper(self, *args, **kwargs):
+        sig = inspect.signature(init)
+        bound = sig.bind(self, *args, **kwargs)
+        bound.apply_defaults()
+        cfg = {k: v for k, v in bound.arguments.items() if k != "self"}
+        object.__setattr__(self, "_vcof_cfg", _Config(cfg))
+        init(self, *args, **kwargs)
+    return wrapper
+
+
+class _ConfigMixin:
+    @property
+    def config(self):
+        return self._vcof_cfg
+
+
+class _ModelMixin(nn.Module):
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+
+class _Dist:
+    def __init__(self, h):
+        self.h = h
+
+    def mode(self):
+        return self.h.chunk(2, dim=1)[0]
+
+
+class _Out:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def __getitem__(self, i):
+        return list(self.__dict__.values())[i]
+
+
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def install_shims():
+    if "diffusers" in sys.modules and getattr(sys.modules["diffusers"], "_vcof_shim", False):
+        return
+
+    class _Log:
+        def get_logger(self, *_a, **_k):
+            import logging as _l
+            return _l.getLogger("ref")
+
+    _mod("diffusers", _vcof_shim=True)
+    _mod("diffusers.configuration_utils", ConfigMixin=_ConfigMixin, register_to_config=_register_to_config)
+    _mod("diffusers.loaders")
+    _mod("diffusers.loaders.single_file_model", FromOriginalModelMixin=type("FromOriginalModelMixin", (), {}))
+    _mod("diffusers.models")
+    _mod("diffusers.models.modeling_utils", ModelMixin=_ModelMixin)
+    _mod("diffusers.models.autoencoders")
+    _mod("diffusers.models.autoencoders.vae", DecoderOutput=lambda sample: _Out(sample=sample),
+         DiagonalGaussianDistribution=_Dist)
+    _mod("diffusers.models.modeling_outputs", AutoencoderKLOutput=lambda latent_dist: _Out(latent_dist=latent_dist))
+    _mod("diffusers.utils", is_torch_version=lambda *_a: True, logging=_Log(), deprecate=lambda *a, **k: None,
+         is_scipy_available=lambda: True)
+    _mod("diffusers.utils.accelerate_utils", apply_forward_hook=lambda f: f)
+    _mod("diffusers.schedulers")
+    _mod("diffusers.schedulers.scheduling_utils", KarrasDiffusionSchedulers=[],
+         SchedulerMixin=type("SchedulerMixin", (), {}),
+         SchedulerOutput=lambda prev_sample: _Out(prev_sample=prev_sample))
+
+
+def _load(modname, relpath):
+    spec = importlib.util.spec_from_file_location(modname, os.path.join(REF, relpath))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+_cache = {}
+
+
+def load_reference():
+    """Returns a namespace with the reference's wan_transformer3d, wan_vae, fm_solvers_unipc modules."""
+    if _cache:
+        return _cache["ns"]
+    if not os.path.isdir(REF):
+        raise RuntimeError(f"{REF} not present: goldens can only be regenerated in the build container")
+    os.environ.setdefault("VIDEOX_ATTENTION_TYPE", "SDPA")  # flash-attn asserts CUDA (attention_utils.py:73)
+    install_shims()
+    pk = _mod("videox_fun")
+    pk.__path__ = []
+    for sub in ("models", "utils", "dist"):
+        m = _mod("videox_fun." + sub)
+        m.__path__ = []
+    d = sys.modules["videox_fun.dist"]
+    for n in ("get_sequence_parallel_rank", "get_sequence_parallel_world_size", "get_sp_group",
+              "usp_attn_forward", "xFuserLongContextAttention"):
+        setattr(d, n, None)
+    cfgopt = _load("videox_fun.utils.cfg_optimization", "videox_fun/utils/cfg_optimization.py")
+    sys.modules["videox_fun.utils"].cfg_skip = cfgopt.cfg_skip
+    _load("videox_fun.models.attention_utils", "videox_fun/models/attention_utils.py")
+    _load("videox_fun.models.cache_utils", "videox_fun/models/cache_utils.py")
+    _mod("videox_fun.models.wan_camera_adapter", SimpleAdapter=None)
+    dit = _load("videox_fun.models.wan_transformer3d", "videox_fun/models/wan_transformer3d.py")
+    vae = _load("videox_fun.models.wan_vae", "videox_fun/models/wan_vae.py")
+    unipc = _load("videox_fun.utils.fm_solvers_unipc", "videox_fun/utils/fm_solvers_unipc.py")
+    ns = types.SimpleNamespace(dit=dit, vae=vae, unipc=unipc)
+    _cache["ns"] = ns
+    return ns
