@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — denoising-steps/s of the VideoCoF hot path (Wan-2.1 14B DiT, 81 f x 720p latents).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl vcof|reference] [--workload c2|c1]
+
+One "step" = the pipeline's per-timestep work (reference videox_fun/pipeline/pipeline_wan.py:694-740):
+DiT forward on the [src | ground | target] latents with chain-of-frames RoPE, zero the source-frame
+velocity, UniPC scheduler step.  Workload C2 (BASELINE.json configs[1]): 14B widths, 40 layers,
+latents [16,21,90,160] -> 75,600 tokens, 4-step fast_infer.py schedule, bf16, random-init weights,
+synthetic latents/prompt embeddings.
+
+Prints ONE JSON line (rank 0).  `value` = steps/s with inputs resident in HBM; `e2e` = the same
+through the public API with HOST (pinned) buffers copied in and the new latents copied out every
+step; `roofline` = the dominant kernel (self-attention) timed live with CUDA events inside the
+timed region; `cpu_baseline` = the CPU oracle timed on this box's host cores on a bounded sample.
+N > 1 (torchrun): sequence-parallel over the ranks, strong scaling.
+`--impl reference` times the reference's CPU implementation (oracle port; /root/reference cannot
+travel to the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (dit config, latent [C,f,h,w], frame_split, n_ctx tokens)
+    "c2": (dict(dim=5120, ffn_dim=13824, num_heads=40, num_layers=40), (16, 21, 90, 160), 10, 77),
+    "c1": (dict(dim=1536, ffn_dim=8960, num_heads=12, num_layers=30), (16, 5, 32, 32), 2, 77),
+}
+METRIC = "denoising_steps_per_sec"
+
+
+def flops_per_forward(cfg, L, S=512):
+    C, F, n = cfg["dim"], cfg["ffn_dim"], cfg["num_layers"]
+    per_block = 8 * L * C * C + 4 * L * L * C + (4 * L * C * C + 4 * S * C * C) + 4 * L * S * C + 4 * L * C * F
+    return per_block * n
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", 1400.0), hbm=d.get("hbm_gbs", 6650.0), src="measured")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port) — bounded sample, extrapolated by token count
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(cfg_kw, L, Ls=1024, Lq=256):
+    """Time ONE oracle block of the workload's widths on this box's cores: token-local ops on Ls tokens,
+    self-attention of Lq queries against all L keys; scale both linearly to L tokens, x layers."""
+    import torch
+    from oracle.dit_oracle import DiTConfig, attention_ref, block_forward, make_block_params, rope_table, \
+        temporal_positions
+    cfg = DiTConfig(**cfg_kw)
+    torch.manual_seed(0)
+    p = make_block_params(cfg, 0, seed=1)
+    C, n, d = cfg.dim, cfg.num_heads, cfg.head_dim
+    x = torch.randn(Ls, C)
+    e0 = torch.randn(6, C) * 0.1
+    ctx = torch.randn(cfg.text_len, C)
+    f, h, w = 1, 1, Ls
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        # token-local part (+ an Ls x Ls attention that is subtracted analytically below)
+        block_forward(p, 0, x, e0, ctx, cfg, (f, h, w), rope_table(d), temporal_positions(f), Ls)
+    t_block = time.perf_counter() - t0
+    q = torch.randn(Lq, n, d)
+    k = torch.randn(L, n, d)
+    v = torch.randn(L, n, d)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for h0 in range(0, n, 8):   # 8 heads at a time bounds the score matrix
+            attention_ref(q[:, h0:h0 + 8], k[:, h0:h0 + 8], v[:, h0:h0 + 8])
+    t_attn = time.perf_counter() - t0
+    # attention inside the block sample cost ~ t_attn * (Ls*Ls)/(Lq*L); remove it from the linear part
+    t_lin = max(t_block - t_attn * (Ls * Ls) / (Lq * L), 0.0)
+    per_block = t_lin * (L / Ls) + t_attn * (L / Lq)
+    step_s = per_block * cfg.num_layers
+    return dict(step_s=step_s, t_block=t_block, t_attn=t_attn, cores=torch.get_num_threads(),
+                sample=f"oracle block ({C}/{cfg.ffn_dim}/{n} heads): token-local ops on {Ls} tokens + "
+                       f"self-attention of {Lq} queries x {L} keys, scaled linearly to {L} tokens x "
+                       f"{cfg.num_layers} layers (extrapolated)")
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path (oracle port) on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg_kw, lat, fs, n_ctx = WORKLOADS[args.workload]
+    L = lat[1] * (lat[2] // 2) * (lat[3] // 2)
+    for _ in range(args.warmup):
+        cpu_reference_sample(cfg_kw, L, Ls=256, Lq=64)
+    vals, last = [], None
+    for _ in range(args.steps):
+        last = cpu_reference_sample(cfg_kw, L)
+        vals.append(last["step_s"])
+    step_s = sum(vals) / len(vals)
+    v = 1.0 / step_s
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, 1),
+            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": last["cores"], "kind": "port",
+                             "sample": last["sample"]},
+            "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(name, n_gpus):
+    cfg_kw, lat, fs, n_ctx = WORKLOADS[name]
+    L = lat[1] * (lat[2] // 2) * (lat[3] // 2)
+    return {"workload": f"{name}: Wan-2.1 DiT dim={cfg_kw['dim']} ffn={cfg_kw['ffn_dim']} heads={cfg_kw['num_heads']} "
+                        f"layers={cfg_kw['num_layers']}, latents {list(lat)} -> {L} tokens, chain-of-frames "
+                        f"{fs}|1|{lat[1] - fs - 1}, 4-step UniPC schedule (shift 3), batch 1",
+            "tokens": L, "parallelism": f"sp{n_gpus}" if n_gpus > 1 else "single",
+            "l2": "working set per layer (>=1.5 GB activations + 0.7 GB weights) >> 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# the libvcof arm
+# ------------------------------------------------------------------------------------------------
+def run_vcof(args):
+    import torch
+    import torch.distributed as dist
+    from videocof_b200 import ops
+    from videocof_b200.dit import WanTransformer3DModel
+    from videocof_b200.scheduler import FlowUniPCMultistepScheduler
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg_kw, lat, fs, n_ctx = WORKLOADS[args.workload]
+    f = lat[1]
+    L = f * (lat[2] // 2) * (lat[3] // 2)
+    model = WanTransformer3DModel.random_init(device=dev, seed=0, **cfg_kw)
+    if world > 1:
+        model.enable_multi_gpus_inference()
+    sched = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, solver_order=2)
+
+    g = torch.Generator(device="cpu").manual_seed(1)
+    lat_host = torch.randn(1, *lat, generator=g).to(torch.bfloat16).pin_memory()
+    ctx_host = torch.randn(n_ctx, 4096, generator=g).to(torch.bfloat16).pin_memory()
+    kw = dict(seq_len=L, frame_split_indices=[fs], ground_frame_indices=[(fs, fs + 1)])
+
+    def new_schedule():
+        sched.set_timesteps(4, device=dev, shift=3.0)
+
+    state = {"latents": lat_host.to(dev), "i": 0}
+    ctx_dev = [ctx_host.to(dev)]
+    new_schedule()
+
+    def one_step(latents, ctx, i):
+        """pipeline_wan.py:700-740 for guidance 1.0 (batch 1)."""
+        if i % 4 == 0:
+            new_schedule()
+        t = sched.timesteps[i % 4]
+        with torch.no_grad():
+            v = model(x=latents, t=t.expand(1), context=ctx, **kw)
+        v[:, :, :fs] = 0
+        return sched.step(v, t, latents, return_dict=False)[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def resident_step():
+        state["latents"] = one_step(state["latents"], ctx_dev, state["i"])
+        state["i"] += 1
+
+    for _ in range(args.warmup):
+        resident_step()
+    state["i"] = 0
+    state["latents"] = lat_host.to(dev)
+    new_schedule()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ops.reset_launches()
+    ops.enable_timing()
+    total_ms = timed(args.steps, resident_step)
+    timing = ops.collect_timing()
+    launches = ops.launches()
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- end to end through the public API with host buffers
+    out_host = torch.empty_like(lat_host)
+    e2e_state = {"i": 0}
+
+    def e2e_step():
+        x = lat_host.to(dev, non_blocking=True)
+        c = [ctx_host.to(dev, non_blocking=True)]
+        y = one_step(x, c, e2e_state["i"])
+        e2e_state["i"] += 1
+        out_host.copy_(y, non_blocking=True)
+
+    new_schedule()
+    e2e_ms = timed(args.steps, e2e_step)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    ms_per_step = total_ms / args.steps
+    value = 1000.0 / ms_per_step
+    peaks = measured_peaks()
+    # dominant kernel: self-attention (72 % of the algorithmic FLOPs at C2)
+    rows = L // world
+    attn_key = [k for k in timing if k.startswith("attn") and f"Lk={L} " in k]
+    roof = None
+    if attn_key:
+        n, ms = timing[attn_key[0]]
+        flops = 4.0 * rows * L * cfg_kw["dim"]
+        ach = flops / (ms / n * 1e-3) / 1e12
+        roof = {"kernel": "attn_fwd_kernel (self-attention)", "bound": "tensor", "achieved": ach,
+                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                "peak_source": f"{peaks['src']} bf16_tflops_sustained", "traffic": None,
+                "flops_per_launch": flops, "avg_launch_ms": ms / n, "launches_timed": n}
+    gpu_ms = sum(ms for _, ms in timing.values())
+    breakdown = sorted(((k, n, ms) for k, (n, ms) in timing.items()), key=lambda r: -r[2])[:8]
+    fl = flops_per_forward(cfg_kw, L)
+    line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args.workload, world),
+            "clocks": clk, "gpu_launches": launches,
+            "e2e": {"value": 1000.0 / (e2e_ms / args.steps), "unit": "steps/s",
+                    "h2d_bytes_per_step": lat_host.numel() * 2 + ctx_host.numel() * 2,
+                    "d2h_bytes_per_step": out_host.numel() * 2},
+            "roofline": roof,
+            "model_tflops": fl / (ms_per_step * 1e-3) / 1e12 / world,
+            "model_frac_of_peak": fl / (ms_per_step * 1e-3) / 1e12 / world / peaks["tflops"],
+            "kernel_ms_per_step": gpu_ms / args.steps,
+            "top_kernels": [{"key": k, "launches": n, "ms": round(ms, 3)} for k, n, ms in breakdown]}
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_sample(cfg_kw, L)
+        line["cpu_baseline"] = {"value": 1.0 / r["step_s"], "unit": "steps/s", "cores": r["cores"],
+                                "kind": "port", "sample": r["sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vcof", choices=["vcof", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_vcof(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

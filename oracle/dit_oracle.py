@@ -22,7 +22,7 @@ import math
 import torch
 
 __all__ = ["DiTConfig", "dit_forward", "block_forward", "rope_table", "temporal_positions",
-           "rope_apply", "sinusoidal_embedding", "make_dit_params", "attention_ref"]
+           "rope_apply", "sinusoidal_embedding", "make_dit_params", "make_block_params", "attention_ref"]
 
 
 class DiTConfig:
@@ -58,56 +58,68 @@ def _rb(x, on):
     return x.to(torch.bfloat16).to(torch.float32) if on else x
 
 
+class _ParamGen:
+    def __init__(self, seed, dtype, bf16_exact):
+        self.g = torch.Generator().manual_seed(seed)
+        self.dtype, self.bf16_exact = dtype, bf16_exact
+        self.p = {}
+
+    def rnd(self, *shape, std=1.0, mean=0.0):
+        t = mean + torch.randn(*shape, generator=self.g, dtype=torch.float32) * std
+        if self.bf16_exact:
+            t = t.to(torch.bfloat16).to(torch.float32)
+        return t.to(self.dtype)
+
+    def lin(self, name, n_out, n_in, std=None, bias_std=0.02):
+        std = std if std is not None else math.sqrt(2.0 / (n_in + n_out))
+        self.p[name + ".weight"] = self.rnd(n_out, n_in, std=std)
+        self.p[name + ".bias"] = self.rnd(n_out, std=bias_std)
+
+    def block(self, cfg, i):
+        C, Fd = cfg.dim, cfg.ffn_dim
+        b = f"blocks.{i}."
+        self.p[b + "modulation"] = self.rnd(1, 6, C, std=1.0 / math.sqrt(C))
+        for attn in ("self_attn", "cross_attn"):
+            for nm in ("q", "k", "v", "o"):
+                self.lin(b + f"{attn}.{nm}", C, C)
+            self.p[b + f"{attn}.norm_q.weight"] = self.rnd(C, std=0.05, mean=1.0)
+            self.p[b + f"{attn}.norm_k.weight"] = self.rnd(C, std=0.05, mean=1.0)
+        self.p[b + "norm3.weight"] = self.rnd(C, std=0.05, mean=1.0)
+        self.p[b + "norm3.bias"] = self.rnd(C, std=0.02)
+        self.lin(b + "ffn.0", Fd, C)
+        self.lin(b + "ffn.2", C, Fd)
+
+
+def make_block_params(cfg, i=0, seed=0, dtype=torch.float32, bf16_exact=True):
+    """Parameters of ONE block only (bench.py cpu_baseline: a 14B block without the embeddings)."""
+    pg = _ParamGen(seed, dtype, bf16_exact)
+    pg.block(cfg, i)
+    return pg.p
+
+
 def make_dit_params(cfg, seed=0, dtype=torch.float32, bf16_exact=True):
     """Deterministic random parameters keyed by the reference's state-dict names.
 
-    Scales follow the reference's init_weights (:1133-1155) except head.head.weight, which the
-    reference zero-initialises (the output would be identically zero).  With bf16_exact the
-    values are bf16-representable so a bf16 model and the fp32 oracle share exact weights.
+    Scales follow the reference's init_weights (:1133-1155) and block modulation init (:462), except
+    head.head.weight, which the reference zero-initialises (the output would be identically zero).
+    With bf16_exact the values are bf16-representable so a bf16 model and the fp32 oracle share
+    exact weights.
     """
-    g = torch.Generator().manual_seed(seed)
-    C, Fd = cfg.dim, cfg.ffn_dim
-    p = {}
-
-    def rnd(*shape, std=1.0):
-        t = torch.randn(*shape, generator=g, dtype=torch.float32) * std
-        if bf16_exact:
-            t = t.to(torch.bfloat16).to(torch.float32)
-        return t.to(dtype)
-
-    def lin(name, n_out, n_in, std=None, bias_std=0.02):
-        std = std if std is not None else math.sqrt(2.0 / (n_in + n_out))
-        p[name + ".weight"] = rnd(n_out, n_in, std=std)
-        p[name + ".bias"] = rnd(n_out, std=bias_std)
-
+    pg = _ParamGen(seed, dtype, bf16_exact)
+    C = cfg.dim
     kin = cfg.in_dim * math.prod(cfg.patch_size)
-    p["patch_embedding.weight"] = rnd(C, cfg.in_dim, *cfg.patch_size, std=math.sqrt(2.0 / (kin + C)))
-    p["patch_embedding.bias"] = rnd(C, std=0.02)
-    lin("text_embedding.0", C, cfg.text_dim, std=0.02)
-    lin("text_embedding.2", C, C, std=0.02)
-    lin("time_embedding.0", C, cfg.freq_dim, std=0.02)
-    lin("time_embedding.2", C, C, std=0.02)
-    lin("time_projection.1", 6 * C, C)
+    pg.p["patch_embedding.weight"] = pg.rnd(C, cfg.in_dim, *cfg.patch_size, std=math.sqrt(2.0 / (kin + C)))
+    pg.p["patch_embedding.bias"] = pg.rnd(C, std=0.02)
+    pg.lin("text_embedding.0", C, cfg.text_dim, std=0.02)
+    pg.lin("text_embedding.2", C, C, std=0.02)
+    pg.lin("time_embedding.0", C, cfg.freq_dim, std=0.02)
+    pg.lin("time_embedding.2", C, C, std=0.02)
+    pg.lin("time_projection.1", 6 * C, C)
     for i in range(cfg.num_layers):
-        b = f"blocks.{i}."
-        p[b + "modulation"] = rnd(1, 6, C, std=1.0 / math.sqrt(C))
-        for attn in ("self_attn", "cross_attn"):
-            for nm in ("q", "k", "v", "o"):
-                lin(b + f"{attn}.{nm}", C, C)
-            p[b + f"{attn}.norm_q.weight"] = 1.0 + rnd(C, std=0.05)
-            p[b + f"{attn}.norm_k.weight"] = 1.0 + rnd(C, std=0.05)
-            if bf16_exact:
-                for nm in ("norm_q", "norm_k"):
-                    k = b + f"{attn}.{nm}.weight"
-                    p[k] = p[k].to(torch.bfloat16).to(dtype)
-        p[b + "norm3.weight"] = (1.0 + rnd(C, std=0.05)).to(torch.bfloat16).to(dtype) if bf16_exact \
-            else 1.0 + rnd(C, std=0.05)
-        p[b + "norm3.bias"] = rnd(C, std=0.02)
-        lin(b + "ffn.0", Fd, C)
-        lin(b + "ffn.2", C, Fd)
-    p["head.modulation"] = rnd(1, 2, C, std=1.0 / math.sqrt(C))
-    lin("head.head", cfg.out_dim * math.prod(cfg.patch_size), C, std=0.02)
-    return p
+        pg.block(cfg, i)
+    pg.p["head.modulation"] = pg.rnd(1, 2, C, std=1.0 / math.sqrt(C))
+    pg.lin("head.head", cfg.out_dim * math.prod(cfg.patch_size), C, std=0.02)
+    return pg.p
 
 
 # --------------------------------------------------------------------------------------

@@ -540,6 +540,40 @@ class WanTransformer3DModel(nn.Module):
                 tc.reset()
         return torch.stack(outs)
 
+    # ---- synthetic weights (bench / smoke: no checkpoints are reachable offline) ------------------------
+    @classmethod
+    def random_init(cls, device="cuda", dtype=torch.bfloat16, seed=0, **config):
+        """Materialise the architecture directly on `device` with random weights of realistic scale
+        (xavier-like Linear weights, N(0,0.02) embeddings/biases, modulation ~ N(0,1/C) as :462;
+        head.head.weight ~ N(0,0.02) instead of the reference's zeros so the output is not 0)."""
+        with torch.device("meta"):
+            model = cls(**config)
+        model.to_empty(device=device)
+        d = model.d
+        model.freqs = torch.cat([rope_params(1024, d - 4 * (d // 6)), rope_params(1024, 2 * (d // 6)),
+                                 rope_params(1024, 2 * (d // 6))], dim=1).to(device)
+        g = torch.Generator(device=device).manual_seed(seed)
+        with torch.no_grad():
+            for name, prm in model.named_parameters():
+                if name.endswith("modulation"):
+                    std = 1.0 / math.sqrt(prm.shape[-1])
+                elif name.endswith(".bias"):
+                    std = 0.02
+                elif name.endswith("norm_q.weight") or name.endswith("norm_k.weight") or name.endswith("norm3.weight"):
+                    prm.data = (1.0 + 0.05 * torch.randn(prm.shape, generator=g, device=device)).to(dtype)
+                    continue
+                elif name.startswith(("text_embedding", "time_embedding", "head.head")):
+                    std = 0.02
+                elif prm.dim() >= 2:
+                    fan_out, fan_in = prm.shape[0], prm[0].numel()
+                    std = math.sqrt(2.0 / (fan_in + fan_out))
+                else:
+                    std = 0.02
+                prm.data = (torch.randn(prm.shape, generator=g, device=device, dtype=torch.float32) * std).to(dtype)
+        for prm in model.parameters():
+            prm.requires_grad_(False)
+        return model.eval()
+
     # ---- loading ---------------------------------------------------------------------------------------
     @classmethod
     def from_config(cls, config, **kwargs):

@@ -26,10 +26,40 @@ def reset_launches():
     _launches = 0
 
 
-def _call(name, *args):
+# optional per-launch CUDA-event timing (bench.py roofline leg / tools/kbench.py)
+_timing = None
+
+
+def enable_timing():
+    """Record a CUDA-event pair around every libvcof launch until collect_timing() is called."""
+    global _timing
+    _timing = []
+
+
+def collect_timing():
+    """-> {key: (launches, total_ms)}; key = kernel name + problem signature.  Synchronises."""
+    global _timing
+    rec, _timing = _timing or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for key, e0, e1 in rec:
+        n, ms = out.get(key, (0, 0.0))
+        out[key] = (n + 1, ms + e0.elapsed_time(e1))
+    return out
+
+
+def _call(name, *args, key=None):
     global _launches
     _launches += 1
+    if _timing is None:
+        _lib.call(name, *args)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
     _lib.call(name, *args)
+    e1.record()
+    _timing.append((key or name, e0, e1))
 
 
 def _p(t):
@@ -84,7 +114,8 @@ def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
     if tuple(out.shape) != (M, N):
         raise _lib.VcofError(f"gemm: out shape {tuple(out.shape)} != {(M, N)}")
     _call("vcof_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _p(bias),
-          _p(gate), out.data_ptr(), out.stride(0), M, N, K, epi, _stream())
+          _p(gate), out.data_ptr(), out.stride(0), M, N, K, epi, _stream(),
+          key=f"gemm[{epilogue}] M={M} N={N} K={K}")
     return out
 
 
@@ -106,7 +137,7 @@ def attention(q, k, v, heads, kv_len=None, scale=None, out=None, v_transposed=Fa
     _chk(out, torch.bfloat16, "attention.out", 2)
     _call("vcof_attn_fwd", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
           v.stride(0), out.data_ptr(), out.stride(0), Lq, Lk, kv_len, heads, hd, float(scale),
-          1 if v_transposed else 0, _stream())
+          1 if v_transposed else 0, _stream(), key=f"attn Lq={Lq} Lk={kv_len} heads={heads}")
     return out
 
 
