@@ -53,3 +53,40 @@ def test_bf16_emulation_close_to_fp32_gold():
                     emulate_bf16=True)
     rel = float((a - b).norm() / a.norm())
     assert rel < 3e-2, rel
+
+
+# ---------------------------------------------------------------------------------------------
+# VAE: the un-chunked closed form of the oracle vs the reference's chunked streaming loop
+# ---------------------------------------------------------------------------------------------
+from gen_golden_vae_impl import VAE_CASES, vae_inputs  # noqa: E402
+from oracle.vae_oracle import VAEConfig, make_vae_params, vae_decode, vae_encode  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def vae_params():
+    return make_vae_params(VAEConfig(), seed=17)
+
+
+@pytest.mark.parametrize("name", list(VAE_CASES))
+def test_vae_oracle_matches_reference_golden(name, golden_dir, vae_params):
+    T, H, W = VAE_CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    assert checksum(vae_params) == pytest.approx(float(gold["param_checksum"]), rel=1e-12)
+    video, z = vae_inputs(T, H, W)
+    cfg = VAEConfig()
+    mu, logvar = vae_encode(vae_params, cfg, video)
+    dec = vae_decode(vae_params, cfg, z)
+    for got, key in ((mu, "mu"), (logvar, "logvar"), (dec, "dec")):
+        ref = torch.from_numpy(gold[key])
+        assert got.shape == ref.shape, (key, got.shape, ref.shape)
+        err = float((got - ref).abs().max())
+        assert err < 5e-5 * max(1.0, float(ref.abs().max())), (name, key, err)
+
+
+def test_vae_decode_is_strictly_causal(vae_params):
+    """decode(z[:, :k]) equals the first 4(k-1)+1 frames of decode(z)."""
+    cfg = VAEConfig()
+    _, z = vae_inputs(13, 16, 16)
+    full = vae_decode(vae_params, cfg, z)
+    part = vae_decode(vae_params, cfg, z[:, :2])
+    assert torch.allclose(full[:, :5], part, atol=1e-5)
