@@ -101,7 +101,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int n_kv = (p.kv_len + kKT - 1) / kKT;
   const int num_items = p.heads * p.num_q_blocks;
 
-  if (warp == 8) {
+  // Register re-balancing between warpgroups: the softmax threads keep a whole 128-wide
+  // score row live, the producer / MMA warpgroup needs almost nothing.
+  if (warp >= 8) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+   if (warp == 8) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       uint32_t item_ph = 0;
@@ -150,7 +154,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (warp == 9) {
+   } else if (warp == 9) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kKT, false, false);
@@ -238,7 +242,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (warp < 8) {
+   }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // =========================== softmax + epilogue ===========================
     const int t = warp >> 2;                         // which Q tile
     const uint32_t lane_base = ((warp & 3) * 32u) << 16;

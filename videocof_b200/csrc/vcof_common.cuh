@@ -104,11 +104,14 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 #define VCOF_SPIN_LIMIT (1u << 24)
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
     if (++spins > VCOF_SPIN_LIMIT) {
+#ifdef VCOF_DEBUG_BARRIERS
       printf("vcof: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x,
              threadIdx.x, bar, parity);
+#endif
       __trap();
     }
   }
