@@ -33,6 +33,7 @@ int vcof_abi_version(void);
 #define VCOF_EPI_BIAS_GELU_BF16 1    /* out_bf16 = bf16(gelu_tanh(bf16(acc + bias)))         */
 #define VCOF_EPI_BIAS_GATE_RES_F32 2 /* out_f32 += gate[n] * bf16(acc + bias)  (gate NULL=1) */
 #define VCOF_EPI_BIAS_F32 3          /* out_f32  = float(bf16(acc + bias))                   */
+#define VCOF_EPI_RAW_F32 4           /* out_f32  = acc + bias (unrounded; attention scores)   */
 
 /* D[M,N] = A[M,K] (bf16) x W[N,K]^T (bf16, nn.Linear layout) with fused epilogue; tcgen05 +
  * TMEM + TMA.  Replaces nn.Linear q/k/v/o, ffn.0/ffn.2, text_embedding, head.head and the
@@ -83,6 +84,44 @@ int vcof_unpatchify(const void* y, long long ldy, void* out, int Cout, int F, in
  * wan_transformer3d.py:668-670, 913-929. */
 int vcof_linear_f32(const float* x, const void* w, const void* bias, float* out, int B, int N, int K,
                     int act_in, int act_out, void* stream);
+
+/* ---- 3D causal VAE (channels-last bf16 activations [T, H, W, C]) ------------------------- */
+
+/* Implicit-GEMM convolution on tcgen05, im2col-free: per filter tap one TMA box of the shifted input
+ * patch feeds the MMA directly; TMA zero-fill provides the spatial and causal-temporal padding.
+ *   x_dims[5]    (c_inner, W, P, H, T) of the input view (P = 1, or 2 for the stride-2 "parity" view
+ *                of the down-sampler where c_inner = 2*Cin); x_strides[4]: element strides of dims 1..4
+ *   w            bf16 [n_total, k_total], k = tap * cin + c  (n_total padded to a multiple of 16)
+ *   taps[5*i..]  (c_base, dw, p, dh, dt): coordinate offsets of tap i added to the tile origin
+ *   geom[16]     T_out, H_out, W_out, t_stride, n_total, n_tile, ot_mul, ot_add, oh_mul, oh_add, ow_mul,
+ *                ow_add, Hs, Ws, interleave_half, n_store — output position (t,h,w) is stored at
+ *                [t*ot_mul+ot_add, h*oh_mul+oh_add, w*ow_mul+ow_add] of a [*, Hs, Ws, ldc] tensor;
+ *                interleave_half > 0 sends channels >= half to the next frame (upsample3d, wan_vae.py:137-141)
+ *   bias fp32 [n_total] | NULL;  residual bf16 (same addressing as out) | NULL;  clamp > 0 clamps.
+ * Replaces CausalConv3d / Conv2d of wan_vae.py:21-40, 80-100, 107-163, 190-224, 318-320, 423-425. */
+int vcof_conv_igemm(const void* x, const long long* x_dims, const long long* x_strides, const void* w,
+                    int k_total, const short* taps, int ntaps, int cin, const int* geom, const float* bias,
+                    const void* residual, void* out, long long ldc, float clamp, void* stream);
+
+/* y = [silu]( x / max(||x||_2, 1e-12) * sqrt(C) * gamma ) per position, channels-last; RMS_norm (+ nn.SiLU)
+ * of wan_vae.py:43-58 with the bf16 rounding points of the reference's ATen op chain. */
+int vcof_rms_silu_cl(const void* x, long long ldx, const float* gamma, void* y, long long ldy,
+                     long long npos, int C, int silu, void* stream);
+
+/* [C, T*H*W] bf16 -> channels-last [T*H*W, Cp] (extra channels zero), optional x/div[c]+add[c]
+ * (latent de-normalisation z / (1/std) + mean, wan_vae.py:553-558). */
+int vcof_nchw_to_cl(const void* x, void* y, int C, int Cp, long long thw, const float* div, const float* add,
+                    void* stream);
+
+/* channels-last [T*H*W, ldx] -> [C, T*H*W] bf16, optional (x - sub[c]) * mul[c] (mu normalisation,
+ * wan_vae.py:540-546). */
+int vcof_cl_to_nchw(const void* x, long long ldx, void* y, int C, long long thw, const float* sub,
+                    const float* mul, void* stream);
+
+/* p_bf16[rows, n] = softmax(s_f32[rows, n] * scale) — the d=384 single-head VAE attention runs as
+ * GEMM (raw fp32 scores) -> this -> GEMM (wan_vae.py:244-266). */
+int vcof_softmax_rows(const float* s, long long lds, void* p, long long ldp, int rows, int n, float scale,
+                      void* stream);
 
 /* ---- diagnostics ---------------------------------------------------------------------- */
 /* One 128x128x64 tcgen05 tile with hand-swizzled operands (no TMA): d_f32[128,128] =

@@ -1,0 +1,108 @@
+"""CPU emulation of the libvcof VAE entry points — an executable statement of the C-ABI contracts in
+include/vcof.h (test infrastructure only).  tests/test_vae_host_cpu.py monkey-patches these over
+videocof_b200.ops so the host-side logic of videocof_b200/vae.py (layer plan, weight packing, tap tables,
+parity views, first-frame rules, frame interleave) is checked against the reference goldens without a GPU.
+"""
+import torch
+
+
+def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
+    acc = a.float() @ w.float().t()
+    if bias is not None:
+        acc = acc + bias.float()
+    if epilogue == "raw_f32":
+        res = acc
+    elif epilogue == "bias":
+        res = acc.to(torch.bfloat16)
+    else:
+        raise NotImplementedError(epilogue)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=None, clamp=0.0):
+    (T, H, W, t_stride, n_total, n_tile, ot_mul, ot_add, oh_mul, oh_add, ow_mul, ow_add, Hs, Ws, half, n_store) = geom
+    C_in, Wd, Pd, Hd, Td = x_dims
+    sW, sP, sH, sT = x_strides
+    flat = x.reshape(-1) if x.is_contiguous() else None
+    base = x.storage_offset()
+    store = x.untyped_storage()
+    full = torch.empty(0, dtype=x.dtype).set_(store)          # whole storage as a flat tensor
+    acc = torch.zeros(T, H, W, n_total)
+    wf = w.float()
+    tt, hh, ww = torch.meshgrid(torch.arange(T), torch.arange(H), torch.arange(W), indexing="ij")
+    cc = torch.arange(cin)
+    for i, (c_base, dw, p, dh, dt) in enumerate(taps):
+        ti = tt * t_stride + dt
+        hi = hh + dh
+        wi = ww + dw
+        ok = (ti >= 0) & (ti < Td) & (hi >= 0) & (hi < Hd) & (wi >= 0) & (wi < Wd) & (0 <= p < Pd)
+        idx = base + ti.clamp(0, Td - 1) * sT + hi.clamp(0, Hd - 1) * sH + p * sP + wi.clamp(0, Wd - 1) * sW
+        ch = c_base + cc
+        ch_ok = ch < C_in
+        gather = full[(idx[..., None] + ch.clamp(max=C_in - 1)[None, None, None, :])].float()
+        gather = gather * ok[..., None] * ch_ok[None, None, None, :]
+        acc += gather @ wf[:, i * cin:(i + 1) * cin].t()
+    if bias is not None:
+        acc = acc + bias
+    for n in range(n_total):
+        fr_add, ns = 0, n
+        if half > 0:
+            if n >= half:
+                fr_add, ns = 1, n - half
+            if ns >= half:
+                continue
+        elif ns >= n_store:
+            continue
+        v = acc[..., n]
+        fr = torch.arange(T) * ot_mul + ot_add + fr_add
+        rows = torch.arange(H) * oh_mul + oh_add
+        cols = torch.arange(W) * ow_mul + ow_add
+        if residual is not None:
+            r = residual[fr][:, rows][:, :, cols][..., ns].float()
+            v = v.to(torch.bfloat16).float() + r
+        if clamp > 0:
+            v = v.clamp(-clamp, clamp)
+        out[fr[:, None, None], rows[None, :, None], cols[None, None, :], ns] = v.to(torch.bfloat16)
+    return out
+
+
+def rms_silu_cl(x, gamma, silu=True, out=None):
+    xf = x.float()
+    dn = xf.pow(2).sum(-1, keepdim=True).sqrt().to(torch.bfloat16).float().clamp_min(1e-12)
+    y = (xf / dn).to(torch.bfloat16).float()
+    y = (y * (x.shape[-1] ** 0.5)).to(torch.bfloat16).float()
+    y = (y * gamma).to(torch.bfloat16).float()
+    if silu:
+        y = torch.nn.functional.silu(y)
+    return y.to(torch.bfloat16)
+
+
+def nchw_to_cl(x, Cp, div=None, add=None):
+    C, T, H, W = x.shape
+    v = x.float()
+    if div is not None:
+        v = ((v / div.view(-1, 1, 1, 1)).to(torch.bfloat16).float() + add.view(-1, 1, 1, 1)).to(torch.bfloat16).float()
+    y = torch.zeros(T, H, W, Cp, dtype=torch.bfloat16)
+    y[..., :C] = v.permute(1, 2, 3, 0).to(torch.bfloat16)
+    return y
+
+
+def cl_to_nchw(x, C, sub=None, mul=None):
+    v = x[..., :C].float()
+    if sub is not None:
+        v = ((v - sub).to(torch.bfloat16).float() * mul).to(torch.bfloat16).float()
+    return v.permute(3, 0, 1, 2).contiguous().to(torch.bfloat16)
+
+
+def softmax_rows(s, scale, out=None):
+    return torch.softmax(s.float() * scale, dim=-1).to(torch.bfloat16)
+
+
+def install(monkeypatch):
+    from videocof_b200 import ops, vae
+    for name in ("gemm", "conv_igemm", "rms_silu_cl", "nchw_to_cl", "cl_to_nchw", "softmax_rows"):
+        monkeypatch.setattr(ops, name, globals()[name])
+    monkeypatch.setattr(vae.AutoencoderKLWan_, "_check", lambda self, x: None)

@@ -104,7 +104,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // Register re-balancing between warpgroups: the softmax threads keep a whole 128-wide
   // score row live, the producer / MMA warpgroup needs almost nothing.
   if (warp >= 8) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
    if (warp == 8) {
     // =========================== TMA producer ===========================
     if (lane == 0) {

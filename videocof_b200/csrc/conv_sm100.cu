@@ -1,0 +1,477 @@
+// conv_sm100.cu — im2col-free implicit-GEMM convolution for the Wan 3D causal VAE on tcgen05 (sm_100a).
+//
+// Activations are channels-last bf16 [T, H, W, C].  An output tile is an 8 x 16 spatial patch of one
+// output frame (128 positions = 128 TMEM lanes) times all (<= 384) output channels.  For every filter
+// tap and every 32-channel slice, ONE TMA box load [32 c, 16 w, 1, 8 h, 1 t] of the *shifted* input
+// patch lands in shared memory already in the canonical K-major 64B-swizzled UMMA layout (128 rows of
+// 64 B), so no im2col buffer ever exists; out-of-range coordinates (spatial zero padding, the causal
+// left padding in time, ragged edges) are zero-filled by the TMA unit.  Weights are pre-packed
+// [Cout, taps * Cin] (tap-major K) and streamed by a second TMA map.
+//
+//   warp 4: TMA producer   warp 5: tcgen05.mma issuer (fp32 accumulators in TMEM, double-buffered
+//   when Cout <= 256)      warps 0-3: epilogue (bias, optional residual, bf16 channels-last store)
+//
+// One kernel covers every convolution of the reference's VAE (videox_fun/models/wan_vae.py):
+//   CausalConv3d 3x3x3 / 1x1x1 (:21-40), the per-frame Conv2d 3x3 of the resamplers (:80-100), the
+//   stride-2 down-sampling Conv2d (5-D "parity" view of the input), the nearest-2x + Conv2d up-sampler
+//   (four parity sub-convolutions with folded 2x2 taps; the 4x tensor is never materialised), and the
+//   (3,1,1) temporal convs of up/down-sampling (:107-163) incl. the frame interleave on store.
+#include "vcof_common.cuh"
+#include "../../include/vcof.h"
+
+namespace vcof {
+
+constexpr int kCvThreads = 192;
+constexpr int kCvStages = 6;
+constexpr int kCvABytes = 128 * 64;          // 128 positions x 32 channels bf16
+constexpr int kCvBBytesMax = 384 * 64;       // up to 384 output channels x 32 k
+constexpr int kCvStage = kCvABytes + kCvBBytesMax;
+constexpr int kCvSmem = kCvStages * kCvStage + 256 + 1024;
+constexpr int kMaxTaps = 27;
+
+constexpr uint64_t kDescSwizzle64 = 4ull << 61;
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw64(uint32_t saddr) {
+  // rows of 64 B, 8-row groups 512 B apart
+  return kDescVersion1 | kDescSwizzle64 | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 16) |
+         uint64_t((saddr & 0x3FFFF) >> 4);
+}
+
+struct ConvTap {
+  short c_base;   // added to the channel coordinate (parity views: pw * Cin)
+  short dw, p, dh, dt;
+};
+
+struct ConvArgs {
+  ConvTap taps[kMaxTaps];
+  int ntaps, cin_chunks;      // K loop = ntaps x cin_chunks slices of 32 channels
+  int cin;                    // padded input channels (multiple of 32): weight K stride per tap
+  int T_out, H_out, W_out;    // logical output grid the tiles walk over
+  int t_stride;               // t_in = t_out * t_stride + dt
+  int n_total, n_tile;        // output channels (padded to 16) and channels per CTA tile (<= 384)
+  // store addressing: frame = t*ot_mul + ot_add (+1 for the second channel half when interleave),
+  // row = h*oh_mul + oh_add, col = w*ow_mul + ow_add inside a [*, Hs, Ws, ldc] tensor
+  int ot_mul, ot_add, oh_mul, oh_add, ow_mul, ow_add, Hs, Ws;
+  long long ldc;
+  int interleave_half;        // > 0: channels >= this go to frame+1 and are stored at (n - half)
+  int n_store;                // channels actually stored per position (<= n_total)
+  const float* bias;          // [n_total] fp32 or nullptr
+  const bf16* residual;       // same addressing as out, or nullptr
+  bf16* out;
+  float clamp;                // > 0: clamp output to [-clamp, clamp]
+};
+
+__global__ void __launch_bounds__(kCvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ ConvArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCvStages * kCvStage);
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * kCvStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kCvStages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kCvStages + 4);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 5) {
+    if (lane == 0) {
+      for (int i = 0; i < kCvStages; ++i) {
+        mbar_init(bar_full + 8 * i, 1);
+        mbar_init(bar_empty + 8 * i, 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_tfull + 8 * i, 1);
+        mbar_init(bar_tempty + 8 * i, 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_w = (p.W_out + 15) / 16, tiles_h = (p.H_out + 7) / 8;
+  const int n_tiles = (p.n_total + p.n_tile - 1) / p.n_tile;
+  const int num_tiles = p.T_out * tiles_h * tiles_w * n_tiles;
+  const int num_k = p.ntaps * p.cin_chunks;
+  const int nacc = (p.n_tile <= 256) ? 2 : 1;            // accumulator buffers in TMEM
+  const int nsub = (p.n_tile <= 256) ? 1 : 2;            // MMAs per k-step (N <= 256 each)
+  const int n_sub = p.n_tile / nsub;
+  const uint32_t b_bytes = p.n_tile * 64;
+
+  auto decode = [&](int tile, int& t, int& h0, int& w0, int& n0) {
+    int nt = tile % n_tiles;
+    int s = tile / n_tiles;
+    w0 = (s % tiles_w) * 16;
+    s /= tiles_w;
+    h0 = (s % tiles_h) * 8;
+    t = s / tiles_h;
+    n0 = nt * p.n_tile;
+  };
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int t, h0, w0, n0;
+        decode(tile, t, h0, w0, n0);
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const ConvTap tp = p.taps[tap];
+          for (int cc = 0; cc < p.cin_chunks; ++cc) {
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            mbar_expect_tx(bar_full + 8 * s, kCvABytes + b_bytes);
+            uint8_t* st = smem + s * kCvStage;
+            tma_load_5d(smem_u32(st), &tmX, bar_full + 8 * s, tp.c_base + cc * 32, w0 + tp.dw, tp.p,
+                        h0 + tp.dh, t * p.t_stride + tp.dt);
+            const int kk = tap * p.cin + cc * 32;
+            for (int j = 0; j < nsub; ++j)
+              tma_load_2d(smem_u32(st + kCvABytes + j * n_sub * 64), &tmW, bar_full + 8 * s, kk,
+                          n0 + j * n_sub);
+            if (++s == kCvStages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, n_sub, false, false);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = (nacc == 2) ? (it & 1) : 0;
+        const uint32_t acc_ph = (nacc == 2) ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int k = 0; k < num_k; ++k) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * kCvStage);
+          const uint32_t b_base = a_base + kCvABytes;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            for (int j = 0; j < nsub; ++j)
+              umma_ss(d_tmem + j * n_sub, make_desc_kmajor_sw64(a_base + ks * 32),
+                      make_desc_kmajor_sw64(b_base + j * n_sub * 64 + ks * 32), idesc, (k | ks) != 0);
+          }
+          umma_commit(bar_empty + 8 * s);
+          if (++s == kCvStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+  } else {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int t, h0, w0, n0;
+      decode(tile, t, h0, w0, n0);
+      const int acc = (nacc == 2) ? (it & 1) : 0;
+      const uint32_t acc_ph = (nacc == 2) ? ((it >> 1) & 1) : (it & 1);
+      mbar_wait(bar_tfull + 8 * acc, acc_ph);
+      tc_fence_after();
+      const int r = warp * 32 + lane;
+      const int h = h0 + (r >> 4), w = w0 + (r & 15);
+      const bool ok = (h < p.H_out) && (w < p.W_out);
+      const long long pos_row = (long long)(h * p.oh_mul + p.oh_add) * p.Ws + (w * p.ow_mul + p.ow_add);
+      const int frame = t * p.ot_mul + p.ot_add;
+      const uint32_t t_row = tmem_base + ((warp * 32u) << 16) + acc * 256;
+      const int n_end = min(p.n_tile, p.n_total - n0);
+#pragma unroll 1
+      for (int c = 0; c < n_end; c += 32) {
+        uint32_t rr[32];
+        tmem_ld32(t_row + c, rr);
+        tmem_ld_wait();
+        if (!ok) continue;
+        const int n = n0 + c;                           // first channel of this 32-chunk
+        int fr = frame, ns = n;
+        if (p.interleave_half > 0 && n >= p.interleave_half) { fr += 1; ns = n - p.interleave_half; }
+        const long long off = ((long long)fr * p.Hs * p.Ws + pos_row) * p.ldc + ns;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+        const int cnt = min(32, min(p.n_total - n, (p.interleave_half > 0 ? p.interleave_half : p.n_store) - ns));
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < cnt) v[j] += __ldg(p.bias + n + j);
+        }
+        if (p.residual != nullptr) {
+          const bf16* rp = p.residual + off;
+          if (cnt == 32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rp + q * 8);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h2[e]);
+                // the reference adds two bf16 tensors: round the conv output first
+                v[q * 8 + e * 2] = bf16_round(v[q * 8 + e * 2]) + f.x;
+                v[q * 8 + e * 2 + 1] = bf16_round(v[q * 8 + e * 2 + 1]) + f.y;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < cnt) v[j] = bf16_round(v[j]) + __bfloat162float(rp[j]);
+          }
+        }
+        if (p.clamp > 0.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -p.clamp), p.clamp);
+        }
+        bf16* o = p.out + off;
+        if (cnt == 32) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            *reinterpret_cast<uint4*>(o + q * 8) = u;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < cnt) o[j] = __float2bfloat16_rn(v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// channels-last helpers (HBM-bound)
+// ---------------------------------------------------------------------------
+// y = silu(x / max(||x||_2, 1e-12) * sqrt(C) * gamma) per position (wan_vae.py:43-58 + nn.SiLU);
+// one warp per position; with silu == 0 the activation is skipped (attention block norm).
+__global__ void rms_silu_cl_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                   bf16* __restrict__ y, long long npos, int C, long long ldx,
+                                   long long ldy, int silu) {
+  const long long pos = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pos >= npos) return;
+  const __nv_bfloat162* xr = reinterpret_cast<const __nv_bfloat162*>(x + pos * ldx);
+  __nv_bfloat162* yr = reinterpret_cast<__nv_bfloat162*>(y + pos * ldy);
+  const int np = C >> 1;
+  float2 v[6];  // C <= 384
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < np) {
+      v[i] = __bfloat1622float2(xr[idx]);
+      sq += v[i].x * v[i].x + v[i].y * v[i].y;
+    }
+  }
+  sq = warp_sum(sq);
+  // F.normalize on a bf16 tensor: norm in fp32 internally, result rounded to bf16, then two bf16
+  // multiplies (* scale, * gamma) as separate ATen ops
+  const float dn = fmaxf(bf16_round(sqrtf(sq)), 1e-12f);
+  const float scale = sqrtf(float(C));
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < np) {
+      float a = bf16_round(bf16_round(bf16_round(v[i].x / dn) * scale) * gamma[2 * idx]);
+      float b = bf16_round(bf16_round(bf16_round(v[i].y / dn) * scale) * gamma[2 * idx + 1]);
+      if (silu) {
+        a = a / (1.f + __expf(-a));
+        b = b / (1.f + __expf(-b));
+      }
+      yr[idx] = __floats2bfloat162_rn(a, b);
+    }
+  }
+}
+
+// [C, T, H, W] (bf16) -> [T, H, W, Cp] channels-last, channels >= C zero-filled; optional per-channel
+// affine x / div[c] + add[c] (latent de-normalisation z / (1/std) + mean, wan_vae.py:553-558).
+__global__ void nchw_to_cl_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int C, int Cp,
+                                  long long thw, const float* __restrict__ mul,
+                                  const float* __restrict__ add) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= thw * Cp) return;
+  const int c = int(i % Cp);
+  const long long pos = i / Cp;
+  float v = 0.f;
+  if (c < C) {
+    v = __bfloat162float(x[(long long)c * thw + pos]);
+    if (mul != nullptr) v = bf16_round(bf16_round(v / mul[c]) + add[c]);
+  }
+  y[i] = __float2bfloat16_rn(v);
+}
+
+// channels-last [T, H, W, ld] -> [C, T, H, W]; optional per-channel affine (x - sub[c]) * mul[c]
+// (latent normalisation of mu, wan_vae.py:540-546).
+__global__ void cl_to_nchw_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int C,
+                                  long long ld, long long thw, const float* __restrict__ sub,
+                                  const float* __restrict__ mul) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= thw * C) return;
+  const long long pos = i % thw;
+  const int c = int(i / thw);
+  float v = __bfloat162float(x[pos * ld + c]);
+  if (sub != nullptr) v = bf16_round(bf16_round(v - sub[c]) * mul[c]);
+  y[i] = __float2bfloat16_rn(v);
+}
+
+// row softmax of fp32 scores -> bf16 probabilities (VAE single-head attention, wan_vae.py:251-256)
+__global__ void softmax_rows_kernel(const float* __restrict__ s, bf16* __restrict__ p, int n,
+                                    long long lds, long long ldp, float scale) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const float* sr = s + row * lds;
+  bf16* pr = p + row * ldp;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, sr[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  mx = __shfl_sync(0xffffffffu, mx, 0);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += __expf((sr[i] - mx) * scale);
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  sum = warp_sum(sum);
+  sum = __shfl_sync(0xffffffffu, sum, 0);
+  const float inv = 1.f / sum;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    pr[i] = __float2bfloat16_rn(__expf((sr[i] - mx) * scale) * inv);
+}
+
+}  // namespace vcof
+
+using namespace vcof;
+
+extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const long long* x_strides,
+                               const void* w, int k_total, const short* taps, int ntaps, int cin,
+                               const int* geom, const float* bias, const void* residual, void* out,
+                               long long ldc, float clamp, void* stream) {
+  // x_dims[5]: (c_inner, W, P, H, T) of the (parity-)view; x_strides[4]: element strides of dims 1..4
+  // geom[14]: T_out,H_out,W_out,t_stride,n_total,n_tile,ot_mul,ot_add,oh_mul,oh_add,ow_mul,ow_add,Hs,Ws
+  //           then [14] interleave_half, [15] n_store
+  VCOF_REQUIRE(ntaps >= 1 && ntaps <= kMaxTaps, "vcof_conv_igemm: ntaps %d outside [1,%d]", ntaps, kMaxTaps);
+  VCOF_REQUIRE(cin % 32 == 0 && cin > 0, "vcof_conv_igemm: cin %d must be a positive multiple of 32", cin);
+  ConvArgs a;
+  for (int i = 0; i < ntaps; ++i) {
+    a.taps[i].c_base = taps[i * 5 + 0];
+    a.taps[i].dw = taps[i * 5 + 1];
+    a.taps[i].p = taps[i * 5 + 2];
+    a.taps[i].dh = taps[i * 5 + 3];
+    a.taps[i].dt = taps[i * 5 + 4];
+  }
+  a.ntaps = ntaps;
+  a.cin = cin;
+  a.cin_chunks = cin / 32;
+  a.T_out = geom[0]; a.H_out = geom[1]; a.W_out = geom[2]; a.t_stride = geom[3];
+  a.n_total = geom[4]; a.n_tile = geom[5];
+  a.ot_mul = geom[6]; a.ot_add = geom[7]; a.oh_mul = geom[8]; a.oh_add = geom[9];
+  a.ow_mul = geom[10]; a.ow_add = geom[11]; a.Hs = geom[12]; a.Ws = geom[13];
+  a.interleave_half = geom[14]; a.n_store = geom[15];
+  a.ldc = ldc;
+  a.bias = bias;
+  a.residual = reinterpret_cast<const bf16*>(residual);
+  a.out = reinterpret_cast<bf16*>(out);
+  a.clamp = clamp;
+  VCOF_REQUIRE(a.n_total % 16 == 0 && a.n_tile % 16 == 0 && a.n_tile <= 384 && a.n_tile >= 16,
+               "vcof_conv_igemm: n_total %d / n_tile %d must be multiples of 16, n_tile <= 384", a.n_total,
+               a.n_tile);
+  VCOF_REQUIRE(a.n_tile <= 256 || (a.n_tile / 2) % 16 == 0, "vcof_conv_igemm: n_tile/2 must be a multiple of 16");
+  VCOF_REQUIRE(k_total == ntaps * cin, "vcof_conv_igemm: weight K %d != ntaps*cin %d", k_total, ntaps * cin);
+  VCOF_REQUIRE(ldc % 8 == 0, "vcof_conv_igemm: ldc must be a multiple of 8");
+  CUtensorMap tmX, tmW;
+  uint64_t dims[5], strides[4];
+  for (int i = 0; i < 5; ++i) dims[i] = (uint64_t)x_dims[i];
+  for (int i = 0; i < 4; ++i) strides[i] = (uint64_t)x_strides[i] * 2;
+  const uint32_t box[5] = {32, 16, 1, 8, 1};
+  int rc = make_tmap_nd_bf16(&tmX, x, 5, dims, strides, box, 64);
+  if (rc) return rc;
+  const int nsub = a.n_tile <= 256 ? 1 : 2;
+  uint64_t wd[2] = {(uint64_t)k_total, (uint64_t)a.n_total};
+  uint64_t ws[1] = {(uint64_t)k_total * 2};
+  uint32_t wb[2] = {32, (uint32_t)(a.n_tile / nsub)};
+  rc = make_tmap_nd_bf16(&tmW, w, 2, wd, ws, wb, 64);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VCOF_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kCvSmem));
+    attr_set = true;
+  }
+  const long long tiles = (long long)a.T_out * ((a.H_out + 7) / 8) * ((a.W_out + 15) / 16) *
+                          ((a.n_total + a.n_tile - 1) / a.n_tile);
+  VCOF_REQUIRE(tiles > 0 && tiles < (1ll << 31), "vcof_conv_igemm: bad tile count %lld", tiles);
+  const int grid = tiles < sm_count() ? (int)tiles : sm_count();
+  conv_igemm_kernel<<<grid, kCvThreads, kCvSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW, a);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vcof_rms_silu_cl(const void* x, long long ldx, const float* gamma, void* y, long long ldy,
+                                long long npos, int C, int silu, void* stream) {
+  VCOF_REQUIRE(C % 2 == 0 && C <= 384 && npos > 0, "vcof_rms_silu_cl: C=%d must be even and <= 384", C);
+  const int threads = 256;
+  const long long blocks = (npos * 32 + threads - 1) / threads;
+  rms_silu_cl_kernel<<<(unsigned)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), gamma, reinterpret_cast<bf16*>(y), npos, C, ldx, ldy, silu);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vcof_nchw_to_cl(const void* x, void* y, int C, int Cp, long long thw, const float* mul,
+                               const float* add, void* stream) {
+  VCOF_REQUIRE(C > 0 && Cp >= C && thw > 0, "vcof_nchw_to_cl: bad shape");
+  const long long n = thw * Cp;
+  nchw_to_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), C, Cp, thw, mul, add);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vcof_cl_to_nchw(const void* x, long long ldx, void* y, int C, long long thw, const float* sub,
+                               const float* mul, void* stream) {
+  VCOF_REQUIRE(C > 0 && thw > 0, "vcof_cl_to_nchw: bad shape");
+  const long long n = thw * C;
+  cl_to_nchw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), C, ldx, thw, sub, mul);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vcof_softmax_rows(const float* s, long long lds, void* p, long long ldp, int rows, int n,
+                                 float scale, void* stream) {
+  VCOF_REQUIRE(rows > 0 && n > 0, "vcof_softmax_rows: empty problem");
+  softmax_rows_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      s, reinterpret_cast<bf16*>(p), n, lds, ldp, scale);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -248,6 +248,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 o[j] += g * bf16_round(v[j]);
               }
           }
+        } else if (EPI == VCOF_EPI_RAW_F32) {  // out = acc + bias, unrounded (attention scores)
+          float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0;
+          if (full_chunk) {
+            float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              o4[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) o[j] = v[j];
+          }
         } else {  // VCOF_EPI_BIAS_F32: out = float(bf16(acc + bias))
           float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0;
           if (full_chunk) {
@@ -307,6 +319,7 @@ static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
     case VCOF_EPI_BIAS_GATE_RES_F32:
       return launch_gemm<BN, VCOF_EPI_BIAS_GATE_RES_F32>(tmA, tmB, args, stream);
     case VCOF_EPI_BIAS_F32: return launch_gemm<BN, VCOF_EPI_BIAS_F32>(tmA, tmB, args, stream);
+    case VCOF_EPI_RAW_F32: return launch_gemm<BN, VCOF_EPI_RAW_F32>(tmA, tmB, args, stream);
   }
   set_last_error("vcof_gemm_bf16: unknown epilogue %d", epi);
   return -1;
@@ -320,9 +333,10 @@ extern "C" int vcof_gemm_bf16(const void* a, long long lda, const void* w, long 
                               const void* bias, const float* gate, void* out, long long ldo, int M,
                               int N, int K, int epilogue, void* stream) {
   VCOF_REQUIRE(M > 0 && N > 0 && K > 0, "vcof_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
-  VCOF_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0,
-               "vcof_gemm_bf16: K/lda/ldw must be multiples of 8 (16-byte TMA rows)");
-  const bool f32_out = (epilogue == VCOF_EPI_BIAS_GATE_RES_F32 || epilogue == VCOF_EPI_BIAS_F32);
+  VCOF_REQUIRE(lda % 8 == 0 && ldw % 8 == 0,
+               "vcof_gemm_bf16: lda/ldw must be multiples of 8 (16-byte TMA rows)");
+  const bool f32_out = (epilogue == VCOF_EPI_BIAS_GATE_RES_F32 || epilogue == VCOF_EPI_BIAS_F32 ||
+                        epilogue == VCOF_EPI_RAW_F32);
   VCOF_REQUIRE(ldo % (f32_out ? 4 : 8) == 0, "vcof_gemm_bf16: ldo=%lld breaks 16-byte row alignment",
                ldo);
   VCOF_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "vcof_gemm_bf16: out not 16B aligned");

@@ -38,7 +38,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }
 
 static int encode(CUtensorMap* map, const void* gptr, uint32_t rank, const uint64_t* dims,
-                  const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   auto fn = encode_fn();
   VCOF_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -57,7 +57,9 @@ static int encode(CUtensorMap* map, const void* gptr, uint32_t rank, const uint6
                  (unsigned long long)gstr[i]);
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(gptr), gdim, gstr,
                   bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VCOF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %u)",
                int(r), rank);
@@ -69,7 +71,7 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* gptr, uint64_t inner, uint64
   uint64_t dims[2] = {inner, outer};
   uint64_t str[1] = {outer_stride_bytes};
   uint32_t box[2] = {box_inner, box_outer};
-  return encode(map, gptr, 2, dims, str, box, true);
+  return encode(map, gptr, 2, dims, str, box, 128);
 }
 
 int make_tmap_3d_bf16(CUtensorMap* map, const void* gptr, uint64_t d0, uint64_t d1, uint64_t d2,
@@ -78,12 +80,12 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* gptr, uint64_t d0, uint64_t 
   uint64_t dims[3] = {d0, d1, d2};
   uint64_t str[2] = {stride1_bytes, stride2_bytes};
   uint32_t box[3] = {b0, b1, b2};
-  return encode(map, gptr, 3, dims, str, box, true);
+  return encode(map, gptr, 3, dims, str, box, 128);
 }
 
-int make_tmap_5d_bf16(CUtensorMap* map, const void* gptr, const uint64_t dims[5],
-                      const uint64_t strides_bytes[4], const uint32_t box[5]) {
-  return encode(map, gptr, 5, dims, strides_bytes, box, true);
+int make_tmap_nd_bf16(CUtensorMap* map, const void* gptr, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  return encode(map, gptr, (uint32_t)rank, dims, strides_bytes, box, swizzle_bytes);
 }
 
 int sm_count() {

@@ -43,8 +43,8 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* gptr, uint64_t inner, uint64
 int make_tmap_3d_bf16(CUtensorMap* map, const void* gptr, uint64_t d0, uint64_t d1, uint64_t d2,
                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
                       uint32_t b2);
-int make_tmap_5d_bf16(CUtensorMap* map, const void* gptr, const uint64_t dims[5],
-                      const uint64_t strides_bytes[4], const uint32_t box[5]);
+int make_tmap_nd_bf16(CUtensorMap* map, const void* gptr, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 int sm_count();
 
 #ifdef __CUDACC__

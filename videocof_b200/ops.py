@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-EPI = {"bias": 0, "bias_gelu": 1, "bias_gate_res": 2, "bias_f32": 3}
+EPI = {"bias": 0, "bias_gelu": 1, "bias_gate_res": 2, "bias_f32": 3, "raw_f32": 4}
 
 # kernel launches since the last reset (bench.py reports it as gpu_launches)
 _launches = 0
@@ -103,7 +103,7 @@ def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
         if out is None:
             raise _lib.VcofError("gemm: bias_gate_res needs the fp32 residual in `out`")
         _chk(out, torch.float32, "gemm.out", 2)
-    elif epi == 3:
+    elif epi in (3, 4):
         if out is None:
             out = torch.empty((M, N), dtype=torch.float32, device=a.device)
         _chk(out, torch.float32, "gemm.out", 2)
@@ -219,4 +219,79 @@ def linear_f32(x, w, bias=None, act_in=False, act_out=False):
     out = torch.empty((B, N), dtype=torch.float32, device=x.device)
     _call("vcof_linear_f32", x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, N, K,
           int(act_in), int(act_out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE ops (channels-last bf16 activations [T, H, W, C])
+# ------------------------------------------------------------------------------------------------
+import ctypes as _ct
+
+
+def _arr(ctype, vals):
+    return (ctype * len(vals))(*vals)
+
+
+def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=None, clamp=0.0):
+    """Raw binding of vcof_conv_igemm (see include/vcof.h).  x: any bf16 CUDA tensor whose storage the
+    5-D view (x_dims / x_strides, elements) addresses from x.data_ptr(); w: packed [n_total, ntaps*cin]."""
+    _chk(x, torch.bfloat16, "conv.x")
+    _chk(w, torch.bfloat16, "conv.w", 2)
+    _chk(out, torch.bfloat16, "conv.out")
+    if bias is not None:
+        _chk(bias, torch.float32, "conv.bias", 1)
+    if residual is not None:
+        _chk(residual, torch.bfloat16, "conv.residual")
+    ntaps = len(taps)
+    flat = [int(v) for tp in taps for v in tp]
+    ldc = out.stride(-2)
+    _call("vcof_conv_igemm", x.data_ptr(), _arr(_ct.c_longlong, [int(v) for v in x_dims]),
+          _arr(_ct.c_longlong, [int(v) for v in x_strides]), w.data_ptr(), w.shape[1],
+          _arr(_ct.c_short, flat), ntaps, cin, _arr(_ct.c_int, [int(v) for v in geom]), _p(bias),
+          _p(residual), out.data_ptr(), ldc, float(clamp), _stream(),
+          key=f"conv taps={ntaps} cin={cin} n={geom[4]} T={geom[0]} H={geom[1]} W={geom[2]}")
+    return out
+
+
+def rms_silu_cl(x, gamma, silu=True, out=None):
+    """Channels-last RMS_norm (+SiLU).  x bf16 [..., C] contiguous rows; gamma fp32 [C]."""
+    _chk(x, torch.bfloat16, "rms_silu.x")
+    _chk(gamma, torch.float32, "rms_silu.gamma", 1)
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    npos = x.numel() // C
+    _call("vcof_rms_silu_cl", x.data_ptr(), x.stride(-2), gamma.data_ptr(), out.data_ptr(), out.stride(-2),
+          npos, C, 1 if silu else 0, _stream())
+    return out
+
+
+def nchw_to_cl(x, Cp, div=None, add=None):
+    """x bf16 [C, T, H, W] -> [T, H, W, Cp] (zero-padded channels); optional x / div[c] + add[c]."""
+    _chk(x, torch.bfloat16, "nchw_to_cl.x", 4)
+    if not x.is_contiguous():
+        raise _lib.VcofError("nchw_to_cl.x must be contiguous")
+    C, T, H, W = x.shape
+    y = torch.empty((T, H, W, Cp), dtype=torch.bfloat16, device=x.device)
+    _call("vcof_nchw_to_cl", x.data_ptr(), y.data_ptr(), C, Cp, T * H * W, _p(div), _p(add), _stream())
+    return y
+
+
+def cl_to_nchw(x, C, sub=None, mul=None):
+    """x bf16 [T, H, W, ld>=C] -> [C, T, H, W]; optional (x - sub[c]) * mul[c]."""
+    _chk(x, torch.bfloat16, "cl_to_nchw.x", 4)
+    T, H, W, ld = x.shape
+    y = torch.empty((C, T, H, W), dtype=torch.bfloat16, device=x.device)
+    _call("vcof_cl_to_nchw", x.data_ptr(), x.stride(2), y.data_ptr(), C, T * H * W, _p(sub), _p(mul), _stream())
+    return y
+
+
+def softmax_rows(s, scale, out=None):
+    """bf16 softmax(s * scale) over the last dim of fp32 s [rows, n]."""
+    _chk(s, torch.float32, "softmax.s", 2)
+    rows, n = s.shape
+    if out is None:
+        out = torch.empty((rows, (n + 7) // 8 * 8), dtype=torch.bfloat16, device=s.device)[:, :n]
+    _call("vcof_softmax_rows", s.data_ptr(), s.stride(0), out.data_ptr(), out.stride(0), rows, n, float(scale),
+          _stream())
     return out

@@ -1,0 +1,553 @@
+"""B200-native Wan-2.1 3D causal VAE with the reference's class API (videox_fun.models.AutoencoderKLWan).
+
+Same module tree / state-dict keys as videox_fun/models/wan_vae.py (reference) — 194 tensors such
+as `model.decoder.upsamples.14.residual.6.weight` — and the same encode()/decode() contract, but
+the compute is un-chunked and channels-last on libvcof kernels:
+
+  * every CausalConv3d / Conv2d runs in the im2col-free tcgen05 implicit-GEMM kernel
+    (`vcof_conv_igemm`): causal time padding, spatial padding and ragged edges come from TMA
+    zero-fill; the stride-2 down-sampler reads a 5-D parity view; nearest-2x + Conv2d is four parity
+    sub-convolutions with folded 2x2 taps (the 4x tensor is never materialised); the temporal
+    up-sampler interleaves its two channel halves into frames on store;
+  * 1x1x1 convolutions are plain tcgen05 GEMMs on the channels-last matrix;
+  * RMS_norm(+SiLU) is one fused HBM pass; the d=384 single-head attention is GEMM -> softmax -> GEMM.
+
+The reference's chunked streaming loop with a 2-frame feature cache (:520-575) is equivalent to these
+un-chunked causal convolutions except for the first-frame rules of the temporal resamplers, which
+are kept (oracle/vae_oracle.py proves the closed form against the reference's own loop).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import VcofError
+
+__all__ = ["AutoencoderKLWan", "AutoencoderKLWan_", "CausalConv3d", "RMS_norm", "Resample", "ResidualBlock",
+           "AttentionBlock", "Encoder3d", "Decoder3d", "DiagonalGaussianDistribution", "DecoderOutput",
+           "AutoencoderKLOutput"]
+
+CACHE_T = 2
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter containers (reference names)
+# ----------------------------------------------------------------------------------------------
+class CausalConv3d(nn.Conv3d):
+    """reference :21-40 (parameters only; padding is realised by TMA zero-fill)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._padding = (self.padding[2], self.padding[2], self.padding[1], self.padding[1], 2 * self.padding[0], 0)
+        self.padding = (0, 0, 0)
+
+
+class RMS_norm(nn.Module):
+    """reference :43-58."""
+
+    def __init__(self, dim, channel_first=True, images=True, bias=False):
+        super().__init__()
+        shape = (dim, *((1, 1) if images else (1, 1, 1))) if channel_first else (dim,)
+        self.channel_first, self.scale = channel_first, dim ** 0.5
+        self.gamma = nn.Parameter(torch.ones(shape))
+        self.bias = nn.Parameter(torch.zeros(shape)) if bias else 0.
+
+
+class Upsample(nn.Upsample):
+    pass
+
+
+class Resample(nn.Module):
+    """reference :70-164."""
+
+    def __init__(self, dim, mode):
+        assert mode in ("none", "upsample2d", "upsample3d", "downsample2d", "downsample3d")
+        super().__init__()
+        self.dim, self.mode = dim, mode
+        if mode in ("upsample2d", "upsample3d"):
+            self.resample = nn.Sequential(Upsample(scale_factor=(2., 2.), mode="nearest-exact"),
+                                          nn.Conv2d(dim, dim // 2, 3, padding=1))
+            if mode == "upsample3d":
+                self.time_conv = CausalConv3d(dim, dim * 2, (3, 1, 1), padding=(1, 0, 0))
+        elif mode in ("downsample2d", "downsample3d"):
+            self.resample = nn.Sequential(nn.ZeroPad2d((0, 1, 0, 1)), nn.Conv2d(dim, dim, 3, stride=(2, 2)))
+            if mode == "downsample3d":
+                self.time_conv = CausalConv3d(dim, dim, (3, 1, 1), stride=(2, 1, 1), padding=(0, 0, 0))
+        else:
+            self.resample = nn.Identity()
+
+
+class ResidualBlock(nn.Module):
+    """reference :190-224."""
+
+    def __init__(self, in_dim, out_dim, dropout=0.0):
+        super().__init__()
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.residual = nn.Sequential(RMS_norm(in_dim, images=False), nn.SiLU(),
+                                      CausalConv3d(in_dim, out_dim, 3, padding=1),
+                                      RMS_norm(out_dim, images=False), nn.SiLU(), nn.Dropout(dropout),
+                                      CausalConv3d(out_dim, out_dim, 3, padding=1))
+        self.shortcut = CausalConv3d(in_dim, out_dim, 1) if in_dim != out_dim else nn.Identity()
+
+
+class AttentionBlock(nn.Module):
+    """reference :227-266."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+        self.norm = RMS_norm(dim)
+        self.to_qkv = nn.Conv2d(dim, dim * 3, 1)
+        self.proj = nn.Conv2d(dim, dim, 1)
+        nn.init.zeros_(self.proj.weight)
+
+
+class Encoder3d(nn.Module):
+    """reference :269-320."""
+
+    def __init__(self, dim=128, z_dim=4, dim_mult=(1, 2, 4, 4), num_res_blocks=2, attn_scales=(),
+                 temperal_downsample=(True, True, False), dropout=0.0):
+        super().__init__()
+        if attn_scales:
+            raise NotImplementedError("attn_scales is empty in every Wan VAE config")
+        dims = [dim * u for u in [1] + list(dim_mult)]
+        self.conv1 = CausalConv3d(3, dims[0], 3, padding=1)
+        layers = []
+        for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+            for _ in range(num_res_blocks):
+                layers.append(ResidualBlock(cin, cout, dropout))
+                cin = cout
+            if i != len(dim_mult) - 1:
+                layers.append(Resample(cout, "downsample3d" if temperal_downsample[i] else "downsample2d"))
+        self.downsamples = nn.Sequential(*layers)
+        self.middle = nn.Sequential(ResidualBlock(cout, cout, dropout), AttentionBlock(cout),
+                                    ResidualBlock(cout, cout, dropout))
+        self.head = nn.Sequential(RMS_norm(cout, images=False), nn.SiLU(), CausalConv3d(cout, z_dim, 3, padding=1))
+
+
+class Decoder3d(nn.Module):
+    """reference :373-425."""
+
+    def __init__(self, dim=128, z_dim=4, dim_mult=(1, 2, 4, 4), num_res_blocks=2, attn_scales=(),
+                 temperal_upsample=(False, True, True), dropout=0.0):
+        super().__init__()
+        dims = [dim * u for u in [dim_mult[-1]] + list(dim_mult[::-1])]
+        self.conv1 = CausalConv3d(z_dim, dims[0], 3, padding=1)
+        self.middle = nn.Sequential(ResidualBlock(dims[0], dims[0], dropout), AttentionBlock(dims[0]),
+                                    ResidualBlock(dims[0], dims[0], dropout))
+        layers = []
+        for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+            if i in (1, 2, 3):
+                cin = cin // 2
+            for _ in range(num_res_blocks + 1):
+                layers.append(ResidualBlock(cin, cout, dropout))
+                cin = cout
+            if i != len(dim_mult) - 1:
+                layers.append(Resample(cout, "upsample3d" if temperal_upsample[i] else "upsample2d"))
+        self.upsamples = nn.Sequential(*layers)
+        self.head = nn.Sequential(RMS_norm(cout, images=False), nn.SiLU(), CausalConv3d(cout, 3, 3, padding=1))
+
+
+# ----------------------------------------------------------------------------------------------
+# weight packing (cached per module, rebuilt when the parameter is mutated)
+# ----------------------------------------------------------------------------------------------
+def _pad32(c):
+    return (c + 31) // 32 * 32
+
+
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def _cached(mod, key, versions, build):
+    cache = mod.__dict__.setdefault("_vcof_pack", {})
+    hit = cache.get(key)
+    if hit is None or hit[0] != versions:
+        cache[key] = (versions, build())
+    return cache[key][1]
+
+
+def _ver(*tensors):
+    return tuple((t.data_ptr(), t._version, str(t.device), t.dtype) for t in tensors if t is not None)
+
+
+def _pack_taps(w_taps, bias, cin_p):
+    """w_taps: fp32 [Cout, Cin, ntaps] -> bf16 [Cout_p16, ntaps*cin_p] (k = tap*cin_p + c), bias fp32 [Cout_p16]."""
+    cout, cin, ntaps = w_taps.shape
+    cout_p = _pad16(cout)
+    w = torch.zeros((cout_p, ntaps, cin_p), dtype=torch.float32, device=w_taps.device)
+    w[:cout, :, :cin] = w_taps.permute(0, 2, 1)
+    b = torch.zeros(cout_p, dtype=torch.float32, device=w_taps.device)
+    if bias is not None:
+        b[:cout] = bias.float()
+    return w.reshape(cout_p, ntaps * cin_p).to(torch.bfloat16).contiguous(), b
+
+
+def pack_conv(conv):
+    """nn.Conv3d [Cout,Cin,kt,kh,kw] / nn.Conv2d [Cout,Cin,kh,kw] -> (packed weight, bias, cin_p); taps ordered
+    (kt, kh, kw)-major."""
+    def build():
+        w = conv.weight.detach().float()
+        w = w.reshape(w.shape[0], w.shape[1], -1)
+        cin_p = _pad32(w.shape[1])
+        pw, pb = _pack_taps(w, conv.bias.detach() if conv.bias is not None else None, cin_p)
+        return pw, pb, cin_p
+    return _cached(conv, "plain", _ver(conv.weight, conv.bias), build)
+
+
+def pack_upsample_conv(conv):
+    """Fold nearest-2x + Conv2d 3x3 (pad 1) into four parity 2x2 convolutions on the low-res input.
+
+    out(2i+ph, 2j+pw) = sum_{dh,dw} W[dh,dw] * in(floor((2i+ph+dh-1)/2), floor((2j+pw+dw-1)/2)); the three
+    taps along each axis collapse onto two source offsets, whose weights are summed (in fp32)."""
+    def build():
+        w = conv.weight.detach().float()          # [Cout, Cin, 3, 3]
+        cin_p = _pad32(w.shape[1])
+        packs = {}
+        # source offset of kernel index d for output parity p: floor((p + d - 1) / 2)
+        for ph in (0, 1):
+            for pw_ in (0, 1):
+                offs_h = sorted({(ph + d - 1) // 2 for d in range(3)})
+                offs_w = sorted({(pw_ + d - 1) // 2 for d in range(3)})
+                taps, mats = [], []
+                for oh in offs_h:
+                    for ow in offs_w:
+                        m = torch.zeros_like(w[:, :, 0, 0])
+                        for dh in range(3):
+                            for dw in range(3):
+                                if (ph + dh - 1) // 2 == oh and (pw_ + dw - 1) // 2 == ow:
+                                    m = m + w[:, :, dh, dw]
+                        mats.append(m)
+                        taps.append((0, ow, 0, oh, 0))
+                wt = torch.stack(mats, dim=2)                      # [Cout, Cin, 4]
+                packs[(ph, pw_)] = _pack_taps(wt, conv.bias.detach(), cin_p) + (taps,)
+        return packs, cin_p
+    return _cached(conv, "up", _ver(conv.weight, conv.bias), build)
+
+
+def _vec(mod, name, t):
+    return _cached(mod, "vec_" + name, _ver(t), lambda: t.detach().float().reshape(-1).contiguous())
+
+
+def _bf(mod, name, t):
+    return _cached(mod, "bf_" + name, _ver(t), lambda: t.detach().to(torch.bfloat16).contiguous())
+
+
+# ----------------------------------------------------------------------------------------------
+# channels-last building blocks: x is bf16 [T, H, W, C] contiguous
+# ----------------------------------------------------------------------------------------------
+def _geom(T, H, W, n_total, n_tile, ot=(1, 0), oh=(1, 0), ow=(1, 0), Hs=None, Ws=None, t_stride=1, half=0,
+          n_store=None):
+    return [T, H, W, t_stride, n_total, n_tile, ot[0], ot[1], oh[0], oh[1], ow[0], ow[1],
+            H if Hs is None else Hs, W if Ws is None else Ws, half, n_total if n_store is None else n_store]
+
+
+def _view5(x):
+    """(dims, strides) of the plain 5-D TMA view (C, W, 1, H, T) of a channels-last tensor."""
+    T, H, W, C = x.shape
+    return (C, W, 1, H, T), (x.stride(2), x.stride(1), x.stride(1), x.stride(0))
+
+
+def _ntile(n_total):
+    return n_total if n_total <= 384 else 384
+
+
+def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None):
+    """CausalConv3d / per-frame Conv2d with 'same' padding, stride 1 (reference :21-40, :142-145)."""
+    pw, pb, cin_p = pack_conv(conv)
+    T, H, W, C = x.shape
+    if C != cin_p:
+        raise VcofError(f"conv input has {C} channels, packed weight expects {cin_p}")
+    k = conv.kernel_size
+    kt, kh, kw = (1, k[0], k[1]) if len(k) == 2 else k
+    taps = [(0, j - kw // 2, 0, i - kh // 2, a - (kt - 1)) for a in range(kt) for i in range(kh) for j in range(kw)]
+    n_total = pw.shape[0]
+    ns = n_total if n_store is None else n_store
+    ldc = (ns + 7) // 8 * 8
+    out = torch.empty((T, H, W, ldc), dtype=torch.bfloat16, device=x.device)
+    if ldc != ns:
+        out.zero_()
+    dims, strides = _view5(x)
+    ops.conv_igemm(x, dims, strides, pw, taps, cin_p, _geom(T, H, W, n_total, _ntile(n_total), n_store=ns), pb, out,
+                   residual=residual, clamp=clamp)
+    return out
+
+
+def conv1x1(x, conv, out_ld=None):
+    """1x1(x1) convolution = GEMM over the channels-last matrix (reference :203-204, :509-510, :236-237)."""
+    T, H, W, C = x.shape
+    w = _cached(conv, "w1x1", _ver(conv.weight), lambda: conv.weight.detach().reshape(conv.weight.shape[0], -1)
+                .to(torch.bfloat16).contiguous())
+    b = _bf(conv, "b1x1", conv.bias)
+    cout = w.shape[0]
+    ld = cout if out_ld is None else out_ld
+    out = torch.zeros((T, H, W, ld), dtype=torch.bfloat16, device=x.device) if ld != cout else \
+        torch.empty((T, H, W, ld), dtype=torch.bfloat16, device=x.device)
+    ops.gemm(x.reshape(-1, C)[:, :w.shape[1]], w, b, "bias", out=out.reshape(-1, ld)[:, :cout])
+    return out
+
+
+def rms_silu(x, norm, silu=True):
+    return ops.rms_silu_cl(x, _vec(norm, "gamma", norm.gamma), silu=silu)
+
+
+def res_block(x, blk):
+    """reference :190-224."""
+    h = x if isinstance(blk.shortcut, nn.Identity) else conv1x1(x, blk.shortcut)
+    y = rms_silu(x, blk.residual[0])
+    y = conv_causal(y, blk.residual[2])
+    y = rms_silu(y, blk.residual[3])
+    return conv_causal(y, blk.residual[6], residual=h)
+
+
+def attn_block(x, blk):
+    """reference :227-266 — per frame, single head, d = C."""
+    T, H, W, C = x.shape
+    n = H * W
+    y = rms_silu(x, blk.norm, silu=False)
+    qkv = conv1x1(y, blk.to_qkv).reshape(T, n, 3 * C)
+    o = torch.empty((T, n, C), dtype=torch.bfloat16, device=x.device)
+    npad = (n + 7) // 8 * 8
+    for t in range(T):
+        q, k, v = qkv[t, :, :C], qkv[t, :, C:2 * C], qkv[t, :, 2 * C:]
+        s = ops.gemm(q, k, None, "raw_f32")
+        p = ops.softmax_rows(s, 1.0 / math.sqrt(C))
+        vt = torch.zeros((C, npad), dtype=torch.bfloat16, device=x.device)
+        vt[:, :n] = v.t()
+        ops.gemm(p, vt[:, :n], None, "bias", out=o[t])
+    a = conv1x1(o.reshape(T, H, W, C), blk.proj)
+    return x + a
+
+
+def downsample(x, rs):
+    """reference :91-100, :147-163."""
+    conv = rs.resample[1]
+    pw, pb, cin_p = pack_conv(conv)
+    T, H, W, C = x.shape
+    H2, W2 = H // 2, W // 2
+    # parity view (c_inner = pw*C + c, w2, ph, h2, t): input row 2*h2 + ph, column 2*w2 + pw
+    dims = (2 * C, W2, 2, H2, T)
+    strides = (2 * x.stride(2), x.stride(1), 2 * x.stride(1), x.stride(0))
+    taps = [((dw % 2) * C, dw // 2, dh % 2, dh // 2, 0) for dh in range(3) for dw in range(3)]
+    n_total = pw.shape[0]
+    y = torch.empty((T, H2, W2, n_total), dtype=torch.bfloat16, device=x.device)
+    ops.conv_igemm(x, dims, strides, pw, taps, cin_p, _geom(T, H2, W2, n_total, _ntile(n_total)), pb, y)
+    if rs.mode == "downsample3d" and T > 1:
+        tw, tb, tcin = pack_conv(rs.time_conv)
+        To = (T - 1) // 2
+        z = torch.empty((1 + To, H2, W2, n_total), dtype=torch.bfloat16, device=x.device)
+        z[0].copy_(y[0])
+        d5, s5 = _view5(y)
+        ttaps = [(0, 0, 0, 0, a) for a in range(3)]
+        ops.conv_igemm(y, d5, s5, tw, ttaps, tcin, _geom(To, H2, W2, n_total, _ntile(n_total), ot=(1, 1), t_stride=2),
+                       tb, z)
+        y = z
+    return y
+
+
+def upsample(x, rs):
+    """reference :80-89, :107-145."""
+    T, H, W, C = x.shape
+    if rs.mode == "upsample3d" and T > 1:
+        tw, tb, tcin = pack_conv(rs.time_conv)                # [2C, 3*C]
+        To = 1 + 2 * (T - 1)
+        z = torch.empty((To, H, W, C), dtype=torch.bfloat16, device=x.device)
+        z[0].copy_(x[0])
+        xs = x[1:]
+        d5, s5 = _view5(xs)
+        ttaps = [(0, 0, 0, 0, a - 2) for a in range(3)]
+        n_total = tw.shape[0]
+        # channels [0,C) -> frame 1+2t, channels [C,2C) -> frame 2+2t
+        ops.conv_igemm(xs, d5, s5, tw, ttaps, tcin, _geom(T - 1, H, W, n_total, _ntile(n_total), ot=(2, 1), half=C),
+                       tb, z)
+        x = z
+        T = To
+    packs, cin_p = pack_upsample_conv(rs.resample[1])
+    cout = rs.resample[1].weight.shape[0]
+    y = torch.empty((T, 2 * H, 2 * W, cout), dtype=torch.bfloat16, device=x.device)
+    d5, s5 = _view5(x)
+    for (ph, pw_), (w4, b4, taps) in packs.items():
+        n_total = w4.shape[0]
+        ops.conv_igemm(x, d5, s5, w4, taps, cin_p,
+                       _geom(T, H, W, n_total, _ntile(n_total), oh=(2, ph), ow=(2, pw_), Hs=2 * H, Ws=2 * W,
+                             n_store=cout), b4, y)
+    return y
+
+
+# ----------------------------------------------------------------------------------------------
+# model
+# ----------------------------------------------------------------------------------------------
+class AutoencoderKLWan_(nn.Module):
+    """reference :487-596 (encode/decode un-chunked; `scale` = [mean, 1/std])."""
+
+    def __init__(self, dim=128, z_dim=4, dim_mult=(1, 2, 4, 4), num_res_blocks=2, attn_scales=(),
+                 temperal_downsample=(True, True, False), dropout=0.0):
+        super().__init__()
+        self.dim, self.z_dim, self.dim_mult = dim, z_dim, list(dim_mult)
+        self.num_res_blocks, self.attn_scales = num_res_blocks, list(attn_scales)
+        self.temperal_downsample = list(temperal_downsample)
+        self.temperal_upsample = self.temperal_downsample[::-1]
+        self.encoder = Encoder3d(dim, z_dim * 2, dim_mult, num_res_blocks, attn_scales, self.temperal_downsample, dropout)
+        self.conv1 = CausalConv3d(z_dim * 2, z_dim * 2, 1)
+        self.conv2 = CausalConv3d(z_dim, z_dim, 1)
+        self.decoder = Decoder3d(dim, z_dim, dim_mult, num_res_blocks, attn_scales, self.temperal_upsample, dropout)
+
+    def _check(self, x):
+        if not x.is_cuda:
+            raise VcofError("AutoencoderKLWan needs CUDA tensors: libvcof has no CPU path")
+        w = self.conv1.weight
+        if w.device != x.device or w.dtype != torch.bfloat16:
+            raise VcofError(f"VAE weights must be bf16 on {x.device} (got {w.dtype} on {w.device}); "
+                            "call .to(device, torch.bfloat16) as the reference CLIs do (fast_infer.py:300-303)")
+
+    @staticmethod
+    def _run(x, layers):
+        for layer in layers:
+            if isinstance(layer, ResidualBlock):
+                x = res_block(x, layer)
+            elif isinstance(layer, AttentionBlock):
+                x = attn_block(x, layer)
+            elif isinstance(layer, Resample):
+                x = downsample(x, layer) if layer.mode.startswith("down") else upsample(x, layer)
+            else:
+                raise VcofError(f"unexpected layer {type(layer)}")
+        return x
+
+    def encode(self, x, scale):
+        """x [1, 3, T, H, W] -> [1, 2*z, f, H/8, W/8] = cat(normalised mu, logvar) (:520-548)."""
+        self._check(x)
+        if x.shape[0] != 1:
+            raise VcofError("encode expects batch 1 (the reference loops over the batch, :647-653)")
+        if (x.shape[2] - 1) % 4 != 0 or x.shape[3] % 8 or x.shape[4] % 8:
+            raise VcofError("video must have 1+4k frames and H, W multiples of 8")
+        enc = self.encoder
+        h = ops.nchw_to_cl(x[0].to(torch.bfloat16).contiguous(), 32)
+        h = conv_causal(h, enc.conv1)
+        h = self._run(h, enc.downsamples)
+        h = self._run(h, enc.middle)
+        h = rms_silu(h, enc.head[0])
+        h = conv_causal(h, enc.head[2])                        # [f, h, w, 32]
+        h = conv1x1(h, self.conv1)
+        z = self.z_dim
+        mean = scale[0].to(x.device, torch.bfloat16).float().contiguous()
+        inv_std = scale[1].to(x.device, torch.bfloat16).float().contiguous()
+        mu = ops.cl_to_nchw(h, z, sub=mean, mul=inv_std)
+        logvar = ops.cl_to_nchw(h[..., z:], z)
+        return torch.cat([mu, logvar], dim=0)[None]
+
+    def decode(self, z, scale):
+        """z [1, 16, f, h, w] (normalised) -> [1, 3, 4(f-1)+1, 8h, 8w] (:550-575); clamp is applied by the caller
+        in the reference (:669) and fused into the last convolution here."""
+        self._check(z)
+        if z.shape[0] != 1:
+            raise VcofError("decode expects batch 1 (the reference loops over the batch, :667-674)")
+        dec = self.decoder
+        mean = scale[0].to(z.device, torch.bfloat16).float().contiguous()
+        inv_std = scale[1].to(z.device, torch.bfloat16).float().contiguous()
+        h = ops.nchw_to_cl(z[0].to(torch.bfloat16).contiguous(), self.z_dim, div=inv_std, add=mean)
+        h = conv1x1(h, self.conv2, out_ld=32)                  # 16 -> 16, stored in a 32-channel (zero padded) tensor
+        h = conv_causal(h, dec.conv1)
+        h = self._run(h, dec.middle)
+        h = self._run(h, dec.upsamples)
+        h = rms_silu(h, dec.head[0])
+        h = conv_causal(h, dec.head[2], clamp=1.0, n_store=3)  # [T, H, W, 8] (3 real channels)
+        return ops.cl_to_nchw(h, 3)[None]
+
+    def clear_cache(self):
+        """The reference's streaming caches do not exist here; kept for API compatibility (:589-596)."""
+
+
+class DiagonalGaussianDistribution:
+    """Enough of diffusers' class for the pipeline: `.mode()` (pipeline_wan.py:407), mean / logvar / sample."""
+
+    def __init__(self, parameters):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def mode(self):
+        return self.mean
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+
+class AutoencoderKLOutput:
+    def __init__(self, latent_dist):
+        self.latent_dist = latent_dist
+
+    def __getitem__(self, i):
+        return (self.latent_dist,)[i]
+
+
+class DecoderOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]
+
+
+class _Config(dict):
+    __getattr__ = dict.get
+
+
+class AutoencoderKLWan(nn.Module):
+    """Drop-in for the reference class (:620-705)."""
+
+    def __init__(self, latent_channels=16, temporal_compression_ratio=4, spatial_compression_ratio=8):
+        super().__init__()
+        self.config = _Config(latent_channels=latent_channels, temporal_compression_ratio=temporal_compression_ratio,
+                              spatial_compression_ratio=spatial_compression_ratio)
+        self.latent_channels = latent_channels
+        self.temporal_compression_ratio = temporal_compression_ratio
+        self.spatial_compression_ratio = spatial_compression_ratio
+        mean = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508,
+                0.4134, -0.0715, 0.5517, -0.3632, -0.1922, -0.9497, 0.2503, -0.2921]
+        std = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743,
+               3.2687, 2.1526, 2.8652, 1.5579, 1.6382, 1.1253, 2.8251, 1.9160]
+        self.mean = torch.tensor(mean, dtype=torch.float32)
+        self.std = torch.tensor(std, dtype=torch.float32)
+        self.scale = [self.mean, 1.0 / self.std]
+        self.model = AutoencoderKLWan_(dim=96, z_dim=latent_channels, dim_mult=[1, 2, 4, 4], num_res_blocks=2,
+                                       attn_scales=[], temperal_downsample=[False, True, True], dropout=0.0)
+
+    @property
+    def dtype(self):
+        return self.model.conv1.weight.dtype
+
+    @property
+    def device(self):
+        return self.model.conv1.weight.device
+
+    def _encode(self, x):
+        return torch.cat([self.model.encode(u.unsqueeze(0), self.scale) for u in x], dim=0)
+
+    def encode(self, x, return_dict=True):
+        posterior = DiagonalGaussianDistribution(self._encode(x))
+        return AutoencoderKLOutput(latent_dist=posterior) if return_dict else (posterior,)
+
+    def _decode(self, zs):
+        return DecoderOutput(sample=torch.cat([self.model.decode(u.unsqueeze(0), self.scale) for u in zs], dim=0))
+
+    def decode(self, z, return_dict=True):
+        decoded = self._decode(z).sample
+        return DecoderOutput(sample=decoded) if return_dict else (decoded,)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, additional_kwargs={}):
+        """reference :684-705 — a single .pth / .safetensors state dict whose keys get the `model.` prefix."""
+        import inspect
+        valid = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        model = cls(**{k: v for k, v in additional_kwargs.items() if k in valid})
+        if pretrained_model_path.endswith(".safetensors"):
+            from safetensors.torch import load_file
+            sd = load_file(pretrained_model_path)
+        else:
+            sd = torch.load(pretrained_model_path, map_location="cpu")
+        m, u = model.load_state_dict({"model." + k: v for k, v in sd.items()}, strict=False)
+        print(f"### missing keys: {len(m)}; \n### unexpected keys: {len(u)};")
+        return model
