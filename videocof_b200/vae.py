@@ -311,7 +311,8 @@ def attn_block(x, blk):
     npad = (n + 7) // 8 * 8
     for t in range(T):
         q, k, v = qkv[t, :, :C], qkv[t, :, C:2 * C], qkv[t, :, 2 * C:]
-        s = ops.gemm(q, k, None, "raw_f32")
+        s = torch.empty((n, npad), dtype=torch.float32, device=x.device)[:, :n]
+        ops.gemm(q, k, None, "raw_f32", out=s)
         p = ops.softmax_rows(s, 1.0 / math.sqrt(C))
         vt = torch.zeros((C, npad), dtype=torch.bfloat16, device=x.device)
         vt[:, :n] = v.t()
