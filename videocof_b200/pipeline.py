@@ -70,9 +70,12 @@ class WanPipeline:
     def maybe_free_model_hooks(self):
         pass
 
-    def enable_model_cpu_offload(self, *a, **k):
-        raise NotImplementedError("CPU offload modes are memory savers for small GPUs; on B200 (180 GB) load the "
-                                  "models with pipeline.to(device) (the CLIs' `else` branch, fast_infer.py:362-363)")
+    def enable_model_cpu_offload(self, gpu_id=None, device="cuda", **_):
+        """The CLIs default to offload modes sized for 24-80 GB GPUs (fast_infer.py:136, :348-361).  A fused path
+        that reads weight pointers directly cannot be paged by accelerate hooks, and a B200 holds the whole
+        pipeline (28 GB DiT + 11 GB T5 + 0.25 GB VAE of 180 GB): keep everything resident instead."""
+        print("[videocof_b200] offload request ignored: keeping DiT / VAE / text encoder resident on", device)
+        return self.to(device)
 
     enable_sequential_cpu_offload = enable_model_cpu_offload
 
