@@ -103,7 +103,7 @@ def test_resamplers_and_norm_vs_contract():
         want = emu.rms_silu_cl(x, g, silu)
         got = ops.rms_silu_cl(x.cuda(), g.cuda(), silu)
         assert rel(got, want) < 3e-3, rel(got, want)
-    s = torch.randn(37, 53) * 3
+    s = torch.randn(37, 533) * 3
     assert rel(ops.softmax_rows(s.cuda(), 0.7), emu.softmax_rows(s, 0.7)) < 3e-3
 
 

@@ -350,7 +350,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, bf16* __restric
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();
-  mx = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
+  mx = ((threadIdx.x & 31) < (blockDim.x >> 5)) ? red[threadIdx.x & 31] : -INFINITY;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   mx = __shfl_sync(0xffffffffu, mx, 0);
@@ -360,7 +360,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, bf16* __restric
   sum = warp_sum(sum);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
   __syncthreads();
-  sum = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  sum = ((threadIdx.x & 31) < (blockDim.x >> 5)) ? red[threadIdx.x & 31] : 0.f;
   sum = warp_sum(sum);
   sum = __shfl_sync(0xffffffffu, sum, 0);
   const float inv = 1.f / sum;
