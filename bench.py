@@ -273,6 +273,37 @@ def run_vcof(args):
     new_schedule()
     e2e_ms = timed(args.steps, e2e_step)
 
+    # ---- whole pipeline through WanPipeline.__call__ (VAE encode -> 4 steps -> VAE decode x2), host in/out
+    pipe_stats = None
+    if world == 1 and not args.no_pipeline:
+        from videocof_b200.pipeline import WanPipeline
+        from videocof_b200.vae import AutoencoderKLWan
+        torch.manual_seed(2)
+        vae = AutoencoderKLWan().to(dev, torch.bfloat16).eval()
+        pipe = WanPipeline(None, None, vae, model, sched)
+        src_frames = 4 * fs - 3                                   # fs latent frames of source video
+        H, W = lat[2] * 8, lat[3] * 8
+        video_host = (torch.rand(1, 3, src_frames, H, W, generator=g) * 2 - 1).to(torch.bfloat16).pin_memory()
+        gen = torch.Generator(device="cpu").manual_seed(4)
+
+        def run_pipe():
+            return pipe(video=video_host, prompt_embeds=[ctx_host.to(dev)], height=H, width=W,
+                        source_frames=src_frames, reasoning_frames=4, num_inference_steps=4, guidance_scale=1.0,
+                        shift=3, repeat_rope=True, cot=True, generator=gen)
+
+        run_pipe()                                                # warm-up (allocator, weight packs)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = run_pipe()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        n_edit = int(out.edit_videos.shape[2])
+        pipe_stats = {"seconds": dt, "frames_per_sec": n_edit / dt, "edit_frames": n_edit,
+                      "ground_frames": int(out.ground_videos.shape[2]), "source_frames": src_frames,
+                      "what": "WanPipeline.__call__: VAE encode(source, host bf16) + 4 DiT steps + VAE decode(ground) + "
+                              "VAE decode(edit) -> fp32 numpy frames on the host; random-init weights"}
+        del vae, pipe, out
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -306,6 +337,7 @@ def run_vcof(args):
             "roofline": roof,
             "model_tflops": fl / (ms_per_step * 1e-3) / 1e12 / world,
             "model_frac_of_peak": fl / (ms_per_step * 1e-3) / 1e12 / world / peaks["tflops"],
+            "pipeline": pipe_stats,
             "kernel_ms_per_step": gpu_ms / args.steps,
             "top_kernels": [{"key": k, "launches": n, "ms": round(ms, 3)} for k, n, ms in breakdown]}
     if world == 1 and not args.no_cpu_baseline:
@@ -326,6 +358,7 @@ def main():
     ap.add_argument("--impl", default="vcof", choices=["vcof", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the WanPipeline (VAE + 4 steps) end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -22,6 +22,8 @@
 // Online softmax uses exp2 with the scale folded in, and a lazy rescale: the
 // running row max is only advanced (and O_t rescaled in TMEM) when it grew by
 // more than 2^8, so in steady state the softmax warps never touch O.
+#include <stdlib.h>
+
 #include "vcof_common.cuh"
 #include "../../include/vcof.h"
 
@@ -71,11 +73,8 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   return r;
 }
 
-#ifndef VCOF_ATTN_EMU_OF8
-#define VCOF_ATTN_EMU_OF8 3  // of every 8 element pairs, this many take the polynomial path
-#endif
-
-template <bool V_TRANS>
+// EMU: of every 8 element pairs, this many take the polynomial path (0 = all MUFU).
+template <bool V_TRANS, int EMU>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
@@ -341,7 +340,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e0]), __uint_as_float(s[e0 + 1])),
                                         sc2, nmb2);
             float2 pr;
-            if ((c & 7) < VCOF_ATTN_EMU_OF8) {
+            if ((c & 7) < EMU) {
               pr = exp2_poly2(x);
             } else {
               pr.x = ex2(x.x);
@@ -434,22 +433,35 @@ extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long l
   const int items = a.heads * a.num_q_blocks;
   const int grid = items < sm_count() ? items : sm_count();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static bool attr_set[2] = {false, false};
-  if (v_transposed) {
-    if (!attr_set[1]) {
-      VCOF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-      attr_set[1] = true;
-    }
-    attn_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, a);
-  } else {
-    if (!attr_set[0]) {
-      VCOF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-      attr_set[0] = true;
-    }
-    attn_fwd_kernel<false><<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, a);
+  // fraction of exponentials evaluated on the FMA pipe; VCOF_ATTN_EMU=0..4 overrides (tuning knob)
+  static int emu = -1;
+  if (emu < 0) {
+    const char* e = getenv("VCOF_ATTN_EMU");
+    emu = e ? atoi(e) : 3;
+    if (emu < 0 || emu > 4) emu = 3;
   }
+  auto launch = [&](auto kern) -> int {
+    VCOF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    kern<<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, a);
+    return 0;
+  };
+  int lrc = 0;
+  if (v_transposed) {
+    switch (emu) {
+      case 0: lrc = launch(attn_fwd_kernel<true, 0>); break;
+      case 2: lrc = launch(attn_fwd_kernel<true, 2>); break;
+      case 4: lrc = launch(attn_fwd_kernel<true, 4>); break;
+      default: lrc = launch(attn_fwd_kernel<true, 3>); break;
+    }
+  } else {
+    switch (emu) {
+      case 0: lrc = launch(attn_fwd_kernel<false, 0>); break;
+      case 2: lrc = launch(attn_fwd_kernel<false, 2>); break;
+      case 4: lrc = launch(attn_fwd_kernel<false, 4>); break;
+      default: lrc = launch(attn_fwd_kernel<false, 3>); break;
+    }
+  }
+  if (lrc) return lrc;
   VCOF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
