@@ -254,7 +254,11 @@ def run_vcof(args):
         clocks.start()
     ops.reset_launches()
     ops.enable_timing()
+    if args.profile_range:
+        torch.cuda.profiler.start()      # ncu --profile-from-start off captures only the timed steps
     total_ms = timed(args.steps, resident_step)
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     timing = ops.collect_timing()
     launches = ops.launches()
     clk = clocks.stop() if rank == 0 else None
@@ -358,6 +362,8 @@ def main():
     ap.add_argument("--impl", default="vcof", choices=["vcof", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps (use with ncu --profile-from-start off)")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the WanPipeline (VAE + 4 steps) end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -98,10 +98,13 @@ int vcof_linear_f32(const float* x, const void* w, const void* bias, float* out,
  *                [t*ot_mul+ot_add, h*oh_mul+oh_add, w*ow_mul+ow_add] of a [*, Hs, Ws, ldc] tensor;
  *                interleave_half > 0 sends channels >= half to the next frame (upsample3d, wan_vae.py:137-141)
  *   bias fp32 [n_total] | NULL;  residual bf16 (same addressing as out) | NULL;  clamp > 0 clamps.
+ *   act_out | NULL: additionally stores silu(rms_norm(result) * act_gamma) — the RMS_norm + SiLU that
+ *                opens the NEXT layer (wan_vae.py:197-201) — with the same addressing; `out` may then be NULL.
  * Replaces CausalConv3d / Conv2d of wan_vae.py:21-40, 80-100, 107-163, 190-224, 318-320, 423-425. */
 int vcof_conv_igemm(const void* x, const long long* x_dims, const long long* x_strides, const void* w,
                     int k_total, const short* taps, int ntaps, int cin, const int* geom, const float* bias,
-                    const void* residual, void* out, long long ldc, float clamp, void* stream);
+                    const void* residual, void* out, long long ldc, float clamp, void* act_out,
+                    const float* act_gamma, void* stream);
 
 /* y = [silu]( x / max(||x||_2, 1e-12) * sqrt(C) * gamma ) per position, channels-last; RMS_norm (+ nn.SiLU)
  * of wan_vae.py:43-58 with the bf16 rounding points of the reference's ATen op chain. */

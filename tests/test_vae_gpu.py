@@ -41,6 +41,8 @@ CONV_CASES = {
     "c3x3x3_96_96_res": dict(cin=96, cout=96, k=(3, 3, 3), T=2, H=9, W=17, res=True),
     "c3x3x3_384_384": dict(cin=384, cout=384, k=(3, 3, 3), T=2, H=8, W=16),
     "c3x3x3_192_384": dict(cin=192, cout=384, k=(3, 3, 3), T=1, H=5, W=7),
+    "c3x3x3_96_96_res_act": dict(cin=96, cout=96, k=(3, 3, 3), T=2, H=9, W=17, res=True, act=True),
+    "c3x3x3_192_384_actonly": dict(cin=192, cout=384, k=(3, 3, 3), T=1, H=8, W=16, act=True, raw=False),
     "head_96_3_clamp": dict(cin=96, cout=3, k=(3, 3, 3), T=2, H=16, W=16, clamp=1.0, n_store=3),
     "time_768": dict(cin=384, cout=768, k=(3, 1, 1), T=3, H=4, W=6),
 }
@@ -57,6 +59,11 @@ def test_conv_igemm_vs_contract(name):
     x = torch.randn(c["T"], c["H"], c["W"], c["cin"]).bfloat16()
     res = torch.randn(c["T"], c["H"], c["W"], (c["cout"] + 7) // 8 * 8).bfloat16() if c.get("res") else None
     kw = dict(clamp=c.get("clamp", 0.0), n_store=c.get("n_store"))
+    norm = None
+    if c.get("act"):
+        norm = vae.RMS_norm(c["cout"], images=False)
+        norm.gamma.data = (torch.rand_like(norm.gamma) + 0.5).bfloat16().float()
+        kw.update(act_norm=norm, want_raw=c.get("raw", True))
     from videocof_b200 import ops
     real = ops.conv_igemm
     # contract (CPU)
@@ -67,9 +74,17 @@ def test_conv_igemm_vs_contract(name):
         ops.conv_igemm = real
     conv_cuda = conv.to("cuda")
     conv_cuda.__dict__.pop("_vcof_pack", None)
+    if norm is not None:
+        norm.__dict__.pop("_vcof_pack", None)
+        kw["act_norm"] = norm.to("cuda")
     got = vae.conv_causal(x.cuda(), conv_cuda, residual=None if res is None else res.cuda(), **kw)
     torch.cuda.synchronize()
-    assert rel(got, want) < 4e-3, rel(got, want)
+    if not isinstance(want, tuple):
+        want, got = (want,), (got,)
+    for g_, w_ in zip(got, want):
+        assert (g_ is None) == (w_ is None)
+        if g_ is not None:
+            assert rel(g_, w_) < 4e-3, rel(g_, w_)
 
 
 def test_resamplers_and_norm_vs_contract():

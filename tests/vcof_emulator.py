@@ -22,7 +22,8 @@ def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
     return res
 
 
-def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=None, clamp=0.0):
+def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=None, clamp=0.0, act_out=None,
+               act_gamma=None):
     (T, H, W, t_stride, n_total, n_tile, ot_mul, ot_add, oh_mul, oh_add, ow_mul, ow_add, Hs, Ws, half, n_store) = geom
     C_in, Wd, Pd, Hd, Td = x_dims
     sW, sP, sH, sT = x_strides
@@ -47,6 +48,9 @@ def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=Non
         acc += gather @ wf[:, i * cin:(i + 1) * cin].t()
     if bias is not None:
         acc = acc + bias
+    if act_out is not None:
+        assert half == 0 and n_tile == n_total
+        final = torch.zeros(T, H, W, n_store)
     for n in range(n_total):
         fr_add, ns = 0, n
         if half > 0:
@@ -65,8 +69,17 @@ def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=Non
             v = v.to(torch.bfloat16).float() + r
         if clamp > 0:
             v = v.clamp(-clamp, clamp)
-        out[fr[:, None, None], rows[None, :, None], cols[None, None, :], ns] = v.to(torch.bfloat16)
-    return out
+        if out is not None:
+            out[fr[:, None, None], rows[None, :, None], cols[None, None, :], ns] = v.to(torch.bfloat16)
+        if act_out is not None:
+            final[..., ns] = v.to(torch.bfloat16).float()
+    if act_out is not None:
+        a = rms_silu_cl(final.to(torch.bfloat16), act_gamma, True)
+        fr = torch.arange(T) * ot_mul + ot_add
+        rows = torch.arange(H) * oh_mul + oh_add
+        cols = torch.arange(W) * ow_mul + ow_add
+        act_out[fr[:, None, None], rows[None, :, None], cols[None, None, :], :n_store] = a
+    return out if out is not None else act_out
 
 
 def rms_silu_cl(x, gamma, silu=True, out=None):

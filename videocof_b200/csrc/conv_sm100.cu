@@ -56,8 +56,10 @@ struct ConvArgs {
   int n_store;                // channels actually stored per position (<= n_total)
   const float* bias;          // [n_total] fp32 or nullptr
   const bf16* residual;       // same addressing as out, or nullptr
-  bf16* out;
+  bf16* out;                  // raw output, may be nullptr when only act_out is wanted
   float clamp;                // > 0: clamp output to [-clamp, clamp]
+  bf16* act_out;              // optional: silu(rms_norm(out) * act_gamma), same addressing as out
+  const float* act_gamma;     // fp32 [n_store]
 };
 
 __global__ void __launch_bounds__(kCvThreads, 1)
@@ -187,20 +189,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int frame = t * p.ot_mul + p.ot_add;
       const uint32_t t_row = tmem_base + ((warp * 32u) << 16) + acc * 256;
       const int n_end = min(p.n_tile, p.n_total - n0);
-#pragma unroll 1
-      for (int c = 0; c < n_end; c += 32) {
+      // one 32-channel chunk: accumulator + bias (+ residual, clamp) -> v[]; returns #valid channels
+      auto chunk = [&](int c, float* v, long long& off, int& n) -> int {
         uint32_t rr[32];
         tmem_ld32(t_row + c, rr);
         tmem_ld_wait();
-        if (!ok) continue;
-        const int n = n0 + c;                           // first channel of this 32-chunk
+        n = n0 + c;
         int fr = frame, ns = n;
         if (p.interleave_half > 0 && n >= p.interleave_half) { fr += 1; ns = n - p.interleave_half; }
-        const long long off = ((long long)fr * p.Hs * p.Ws + pos_row) * p.ldc + ns;
-        float v[32];
+        off = ((long long)fr * p.Hs * p.Ws + pos_row) * p.ldc + ns;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
         const int cnt = min(32, min(p.n_total - n, (p.interleave_half > 0 ? p.interleave_half : p.n_store) - ns));
+        if (!ok) return 0;
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -231,7 +232,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -p.clamp), p.clamp);
         }
-        bf16* o = p.out + off;
+        return cnt;
+      };
+      auto store = [&](bf16* o, const float* v, int cnt) {
         if (cnt == 32) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -246,6 +249,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (j < cnt) o[j] = __float2bfloat16_rn(v[j]);
+        }
+      };
+      float sq = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < n_end; c += 32) {
+        float v[32];
+        long long off;
+        int n;
+        const int cnt = chunk(c, v, off, n);
+        if (cnt <= 0) continue;
+        if (p.out != nullptr) store(p.out + off, v, cnt);
+        if (p.act_out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < cnt) { const float r = bf16_round(v[j]); sq += r * r; }
+        }
+      }
+      if (p.act_out != nullptr) {
+        // fused RMS_norm + SiLU of the NEXT layer (wan_vae.py:43-58): needs the whole channel row, which
+        // one thread owns because n_tile == n_total; second pass over TMEM instead of 384 live registers
+        const float dn = fmaxf(bf16_round(sqrtf(sq)), 1e-12f);
+        const float scale = sqrtf(float(p.n_store));
+#pragma unroll 1
+        for (int c = 0; c < n_end; c += 32) {
+          float v[32];
+          long long off;
+          int n;
+          const int cnt = chunk(c, v, off, n);
+          if (cnt <= 0) continue;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < cnt) {
+              float a = bf16_round(bf16_round(bf16_round(bf16_round(v[j]) / dn) * scale) * __ldg(p.act_gamma + n + j));
+              v[j] = a / (1.f + __expf(-a));
+            }
+          }
+          store(p.act_out + off, v, cnt);
         }
       }
       tc_fence_before();
@@ -375,7 +415,8 @@ using namespace vcof;
 extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const long long* x_strides,
                                const void* w, int k_total, const short* taps, int ntaps, int cin,
                                const int* geom, const float* bias, const void* residual, void* out,
-                               long long ldc, float clamp, void* stream) {
+                               long long ldc, float clamp, void* act_out, const float* act_gamma,
+                               void* stream) {
   // x_dims[5]: (c_inner, W, P, H, T) of the (parity-)view; x_strides[4]: element strides of dims 1..4
   // geom[14]: T_out,H_out,W_out,t_stride,n_total,n_tile,ot_mul,ot_add,oh_mul,oh_add,ow_mul,ow_add,Hs,Ws
   //           then [14] interleave_half, [15] n_store
@@ -402,6 +443,11 @@ extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const lon
   a.residual = reinterpret_cast<const bf16*>(residual);
   a.out = reinterpret_cast<bf16*>(out);
   a.clamp = clamp;
+  a.act_out = reinterpret_cast<bf16*>(act_out);
+  a.act_gamma = act_gamma;
+  VCOF_REQUIRE(out != nullptr || act_out != nullptr, "vcof_conv_igemm: no output requested");
+  VCOF_REQUIRE(act_out == nullptr || (act_gamma != nullptr && a.n_tile == a.n_total && a.interleave_half == 0),
+               "vcof_conv_igemm: fused norm needs gamma, a single channel tile and no frame interleave");
   VCOF_REQUIRE(a.n_total % 16 == 0 && a.n_tile % 16 == 0 && a.n_tile <= 384 && a.n_tile >= 16,
                "vcof_conv_igemm: n_total %d / n_tile %d must be multiples of 16, n_tile <= 384", a.n_total,
                a.n_tile);

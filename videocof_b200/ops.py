@@ -232,25 +232,33 @@ def _arr(ctype, vals):
     return (ctype * len(vals))(*vals)
 
 
-def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=None, clamp=0.0):
+def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=None, clamp=0.0, act_out=None,
+               act_gamma=None):
     """Raw binding of vcof_conv_igemm (see include/vcof.h).  x: any bf16 CUDA tensor whose storage the
     5-D view (x_dims / x_strides, elements) addresses from x.data_ptr(); w: packed [n_total, ntaps*cin]."""
     _chk(x, torch.bfloat16, "conv.x")
     _chk(w, torch.bfloat16, "conv.w", 2)
-    _chk(out, torch.bfloat16, "conv.out")
+    ref_out = out if out is not None else act_out
+    _chk(ref_out, torch.bfloat16, "conv.out")
+    if act_out is not None:
+        _chk(act_out, torch.bfloat16, "conv.act_out")
+        _chk(act_gamma, torch.float32, "conv.act_gamma", 1)
+        if out is not None and act_out.stride(-2) != out.stride(-2):
+            raise _lib.VcofError("conv: out and act_out must share the position pitch")
     if bias is not None:
         _chk(bias, torch.float32, "conv.bias", 1)
     if residual is not None:
         _chk(residual, torch.bfloat16, "conv.residual")
     ntaps = len(taps)
     flat = [int(v) for tp in taps for v in tp]
-    ldc = out.stride(-2)
+    ldc = ref_out.stride(-2)
     _call("vcof_conv_igemm", x.data_ptr(), _arr(_ct.c_longlong, [int(v) for v in x_dims]),
           _arr(_ct.c_longlong, [int(v) for v in x_strides]), w.data_ptr(), w.shape[1],
           _arr(_ct.c_short, flat), ntaps, cin, _arr(_ct.c_int, [int(v) for v in geom]), _p(bias),
-          _p(residual), out.data_ptr(), ldc, float(clamp), _stream(),
-          key=f"conv taps={ntaps} cin={cin} n={geom[4]} T={geom[0]} H={geom[1]} W={geom[2]}")
-    return out
+          _p(residual), _p(out), ldc, float(clamp), _p(act_out), _p(act_gamma), _stream(),
+          key=f"conv taps={ntaps} cin={cin} n={geom[4]} T={geom[0]} H={geom[1]} W={geom[2]}"
+              + ("+act" if act_out is not None else ""))
+    return ref_out
 
 
 def rms_silu_cl(x, gamma, silu=True, out=None):

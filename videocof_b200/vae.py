@@ -253,8 +253,11 @@ def _ntile(n_total):
     return n_total if n_total <= 384 else 384
 
 
-def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None):
-    """CausalConv3d / per-frame Conv2d with 'same' padding, stride 1 (reference :21-40, :142-145)."""
+def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None, act_norm=None, want_raw=True):
+    """CausalConv3d / per-frame Conv2d with 'same' padding, stride 1 (reference :21-40, :142-145).
+
+    act_norm: an RMS_norm module whose norm+SiLU (the opening of the NEXT layer) is fused into the epilogue;
+    returns (raw, act) then (raw is None when want_raw is False)."""
     pw, pb, cin_p = pack_conv(conv)
     T, H, W, C = x.shape
     if C != cin_p:
@@ -265,12 +268,20 @@ def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None):
     n_total = pw.shape[0]
     ns = n_total if n_store is None else n_store
     ldc = (ns + 7) // 8 * 8
+    dims, strides = _view5(x)
+    geom = _geom(T, H, W, n_total, _ntile(n_total), n_store=ns)
+    if act_norm is not None and n_total <= 384:
+        out = torch.empty((T, H, W, ldc), dtype=torch.bfloat16, device=x.device) if want_raw else None
+        act = torch.empty((T, H, W, ldc), dtype=torch.bfloat16, device=x.device)
+        ops.conv_igemm(x, dims, strides, pw, taps, cin_p, geom, pb, out, residual=residual, clamp=clamp,
+                       act_out=act, act_gamma=_vec(act_norm, "gamma", act_norm.gamma))
+        return out, act
     out = torch.empty((T, H, W, ldc), dtype=torch.bfloat16, device=x.device)
     if ldc != ns:
         out.zero_()
-    dims, strides = _view5(x)
-    ops.conv_igemm(x, dims, strides, pw, taps, cin_p, _geom(T, H, W, n_total, _ntile(n_total), n_store=ns), pb, out,
-                   residual=residual, clamp=clamp)
+    ops.conv_igemm(x, dims, strides, pw, taps, cin_p, geom, pb, out, residual=residual, clamp=clamp)
+    if act_norm is not None:
+        return out, rms_silu(out, act_norm)
     return out
 
 
@@ -292,13 +303,16 @@ def rms_silu(x, norm, silu=True):
     return ops.rms_silu_cl(x, _vec(norm, "gamma", norm.gamma), silu=silu)
 
 
-def res_block(x, blk):
-    """reference :190-224."""
+def res_block(x, blk, x_act=None, next_norm=None):
+    """reference :190-224.  x_act = silu(rms_norm(x)) if the producer already fused it; with next_norm the
+    block returns (y, silu(rms_norm_next(y))) from the last conv's epilogue."""
     h = x if isinstance(blk.shortcut, nn.Identity) else conv1x1(x, blk.shortcut)
-    y = rms_silu(x, blk.residual[0])
-    y = conv_causal(y, blk.residual[2])
-    y = rms_silu(y, blk.residual[3])
-    return conv_causal(y, blk.residual[6], residual=h)
+    if x_act is None:
+        x_act = rms_silu(x, blk.residual[0])
+    _, y_act = conv_causal(x_act, blk.residual[2], act_norm=blk.residual[3], want_raw=False)
+    if next_norm is None:
+        return conv_causal(y_act, blk.residual[6], residual=h), None
+    return conv_causal(y_act, blk.residual[6], residual=h, act_norm=next_norm)
 
 
 def attn_block(x, blk):
@@ -403,17 +417,23 @@ class AutoencoderKLWan_(nn.Module):
                             "call .to(device, torch.bfloat16) as the reference CLIs do (fast_infer.py:300-303)")
 
     @staticmethod
-    def _run(x, layers):
-        for layer in layers:
+    def _run(x, layers, x_act=None, tail_norm=None):
+        """Walk a layer list.  RMS_norm+SiLU that opens a ResidualBlock (or `tail_norm`, the head's norm) is
+        produced by the previous ResidualBlock's last convolution when there is one."""
+        layers = list(layers)
+        for i, layer in enumerate(layers):
+            nxt = layers[i + 1] if i + 1 < len(layers) else None
+            next_norm = nxt.residual[0] if isinstance(nxt, ResidualBlock) else (tail_norm if nxt is None else None)
             if isinstance(layer, ResidualBlock):
-                x = res_block(x, layer)
+                x, x_act = res_block(x, layer, x_act, next_norm)
             elif isinstance(layer, AttentionBlock):
-                x = attn_block(x, layer)
+                x, x_act = attn_block(x, layer), None
             elif isinstance(layer, Resample):
                 x = downsample(x, layer) if layer.mode.startswith("down") else upsample(x, layer)
+                x_act = None
             else:
                 raise VcofError(f"unexpected layer {type(layer)}")
-        return x
+        return x, x_act
 
     def encode(self, x, scale):
         """x [1, 3, T, H, W] -> [1, 2*z, f, H/8, W/8] = cat(normalised mu, logvar) (:520-548)."""
@@ -425,10 +445,11 @@ class AutoencoderKLWan_(nn.Module):
         enc = self.encoder
         h = ops.nchw_to_cl(x[0].to(torch.bfloat16).contiguous(), 32)
         h = conv_causal(h, enc.conv1)
-        h = self._run(h, enc.downsamples)
-        h = self._run(h, enc.middle)
-        h = rms_silu(h, enc.head[0])
-        h = conv_causal(h, enc.head[2])                        # [f, h, w, 32]
+        h, a = self._run(h, enc.downsamples)
+        h, a = self._run(h, enc.middle, a, tail_norm=enc.head[0])
+        if a is None:
+            a = rms_silu(h, enc.head[0])
+        h = conv_causal(a, enc.head[2])                        # [f, h, w, 32]
         h = conv1x1(h, self.conv1)
         z = self.z_dim
         mean = scale[0].to(x.device, torch.bfloat16).float().contiguous()
@@ -449,10 +470,11 @@ class AutoencoderKLWan_(nn.Module):
         h = ops.nchw_to_cl(z[0].to(torch.bfloat16).contiguous(), self.z_dim, div=inv_std, add=mean)
         h = conv1x1(h, self.conv2, out_ld=32)                  # 16 -> 16, stored in a 32-channel (zero padded) tensor
         h = conv_causal(h, dec.conv1)
-        h = self._run(h, dec.middle)
-        h = self._run(h, dec.upsamples)
-        h = rms_silu(h, dec.head[0])
-        h = conv_causal(h, dec.head[2], clamp=1.0, n_store=3)  # [T, H, W, 8] (3 real channels)
+        h, a = self._run(h, dec.middle)
+        h, a = self._run(h, dec.upsamples, a, tail_norm=dec.head[0])
+        if a is None:
+            a = rms_silu(h, dec.head[0])
+        h = conv_causal(a, dec.head[2], clamp=1.0, n_store=3)  # [T, H, W, 8] (3 real channels)
         return ops.cl_to_nchw(h, 3)[None]
 
     def clear_cache(self):
