@@ -1,0 +1,113 @@
+"""Host-side plumbing of videocof_b200.pipeline.WanPipeline on CPU with stub DiT / VAE modules: chain-of-frames
+latent assembly, frame-split kwargs, CFG batching, frozen source frames, split ground/edit decode
+(reference videox_fun/pipeline/pipeline_wan.py:381-428, 592-799)."""
+import numpy as np
+import torch
+
+from videocof_b200.pipeline import WanPipeline, randn_tensor
+from videocof_b200.scheduler import FlowUniPCMultistepScheduler
+
+
+class _Cfg(dict):
+    __getattr__ = dict.get
+
+
+class StubVAE:
+    temporal_compression_ratio = 4
+    spatial_compression_ratio = 8
+    latent_channels = 16
+    dtype = torch.float32
+
+    class _D:
+        def __init__(self, m):
+            self.m = m
+
+        def mode(self):
+            return self.m
+
+    def encode(self, x):
+        b, _, t, h, w = x.shape
+        f = (t - 1) // 4 + 1
+        return (self._D(torch.full((b, 16, f, h // 8, w // 8), 0.5)),)
+
+    def decode(self, z):
+        b, _, f, h, w = z.shape
+        out = z.mean(dim=1, keepdim=True).repeat_interleave(4, dim=2)[:, :, :4 * (f - 1) + 1]
+        out = out.repeat(1, 3, 1, 1, 1).repeat_interleave(8, 3).repeat_interleave(8, 4)
+
+        class O:
+            sample = out
+        return O
+
+
+class StubDiT:
+    config = _Cfg(in_channels=16, patch_size=(1, 2, 2))
+    dtype = torch.float32
+    device = torch.device("cpu")
+
+    def __init__(self):
+        self.calls = []
+        self.num_inference_steps = None
+        self.current_steps = 0
+
+    def __call__(self, x, t, context, seq_len, frame_split_indices=None, ground_frame_indices=None):
+        self.calls.append(dict(shape=tuple(x.shape), t=t.clone(), n_ctx=len(context), seq_len=seq_len,
+                               fsi=frame_split_indices, gfi=ground_frame_indices, step=self.current_steps))
+        return torch.ones_like(x) * (1 + torch.arange(x.shape[0]).view(-1, 1, 1, 1, 1))
+
+
+def make(guidance):
+    dit, vae = StubDiT(), StubVAE()
+    pipe = WanPipeline(None, None, vae, dit, FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1))
+    video = torch.zeros(1, 3, 9, 32, 48)                       # 9 source frames -> 3 latent frames
+    emb = [torch.randn(5, 8)]
+    out = pipe(video=video, prompt_embeds=emb, negative_prompt_embeds=[torch.randn(3, 8)] if guidance > 1 else None,
+               height=32, width=48, source_frames=9, reasoning_frames=4, num_inference_steps=4,
+               guidance_scale=guidance, shift=3, repeat_rope=True, cot=True, generator=torch.Generator().manual_seed(0))
+    return dit, out
+
+
+def test_cot_layout_and_kwargs():
+    dit, out = make(1.0)
+    assert len(dit.calls) == 4
+    c = dit.calls[0]
+    assert c["shape"] == (1, 16, 3 + 1 + 3, 4, 6)             # [src 3 | ground 1 | target 3]
+    assert c["fsi"] == [3] and c["gfi"] == [(3, 4)]
+    assert c["seq_len"] == 7 * 2 * 3
+    assert [int(k["t"][0]) for k in dit.calls] == [999, 899, 749, 499]
+    assert [k["step"] for k in dit.calls] == [0, 1, 2, 3]
+    # ground segment: 1 latent -> 1 frame; edit segment: 3 latents -> 9 frames; concatenated along time
+    assert tuple(out.ground_videos.shape) == (1, 3, 1, 32, 48)
+    assert tuple(out.edit_videos.shape) == (1, 3, 9, 32, 48)
+    assert tuple(out.videos.shape) == (1, 3, 10, 32, 48)
+    assert float(out.videos.min()) >= 0.0 and float(out.videos.max()) <= 1.0
+
+
+def test_cfg_batches_two_and_combines():
+    dit, _ = make(5.0)
+    assert dit.calls[0]["shape"][0] == 2 and dit.calls[0]["n_ctx"] == 2
+    assert dit.calls[0]["fsi"] == [3, 3]
+
+
+def test_source_frames_keep_their_latents():
+    """noise_pred[:, :, :condition_count] = 0 (:736): UniPC with zero velocity leaves x unchanged."""
+    dit, vae = StubDiT(), StubVAE()
+    sched = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1)
+    pipe = WanPipeline(None, None, vae, dit, sched)
+    seen = {}
+
+    def cb(p, i, t, kw):
+        seen[i] = kw["latents"].clone()
+        return {}
+    pipe(video=torch.zeros(1, 3, 5, 16, 16), prompt_embeds=[torch.randn(2, 8)], height=16, width=16, source_frames=5,
+         reasoning_frames=4, num_inference_steps=4, guidance_scale=1.0, shift=3, cot=True, callback_on_step_end=cb,
+         generator=torch.Generator().manual_seed(1))
+    for i in range(4):
+        assert torch.allclose(seen[i][:, :, :2], torch.full_like(seen[i][:, :, :2], 0.5))   # encoded source = 0.5
+    assert not torch.allclose(seen[3][:, :, 2:], seen[0][:, :, 2:])
+
+
+def test_randn_tensor_cpu_generator_is_device_independent():
+    a = randn_tensor((2, 3), generator=torch.Generator().manual_seed(3), device="cpu", dtype=torch.float32)
+    b = torch.randn((2, 3), generator=torch.Generator().manual_seed(3))
+    assert torch.equal(a, b)

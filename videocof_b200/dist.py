@@ -25,6 +25,7 @@ class SequenceParallel:
         self.kv_len = None
         self.rows = None
         self._kg = self._vg = None
+        self._pending = {}
         if attn_fn is None:
             from . import ops
             attn_fn = ops.attention
@@ -47,13 +48,25 @@ class SequenceParallel:
             setattr(self, name, buf)
         return buf
 
+    def start_gather(self, which, x):
+        """Launch the all-gather of this rank's K (or V) shard asynchronously: NCCL runs on its own stream
+        once the producing kernels have finished, and overlaps whatever the compute stream does next (the
+        V / Q projections); `attention_gathered` waits for it."""
+        buf = self._gather_buf("_kg" if which == "k" else "_vg", x)
+        work = dist.all_gather_into_tensor(buf, x.contiguous(), group=self.group, async_op=True)
+        self._pending[which] = (buf, work)
+
+    def attention_gathered(self, q, heads, out=None):
+        (kg, wk), (vg, wv) = self._pending.pop("k"), self._pending.pop("v")
+        wk.wait()
+        wv.wait()
+        return self.attn_fn(q, kg, vg, heads, kv_len=self.kv_len, out=out)
+
     def attention(self, q, k, v, heads, out=None):
         """Local queries against the all-gathered keys/values (keys beyond kv_len are padding)."""
-        kg = self._gather_buf("_kg", k)
-        vg = self._gather_buf("_vg", v)
-        dist.all_gather_into_tensor(kg, k.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(vg, v.contiguous(), group=self.group)
-        return self.attn_fn(q, kg, vg, heads, kv_len=self.kv_len, out=out)
+        self.start_gather("k", k)
+        self.start_gather("v", v)
+        return self.attention_gathered(q, heads, out=out)
 
     def all_gather_rows(self, y):
         full = torch.empty((self.world * y.shape[0],) + tuple(y.shape[1:]), dtype=y.dtype, device=y.device)

@@ -120,15 +120,23 @@ class WanAttentionBlock(nn.Module):
         n, hd = self.num_heads, self.dim // self.num_heads
         # self-attention (:495-499)
         ops.ln_modulate(x, None, None, e[0], e[1], self.eps, out=ws.a)
-        ops.gemm(ws.a, sa.q.weight, sa.q.bias, "bias", out=ws.q)
-        ops.gemm(ws.a, sa.k.weight, sa.k.bias, "bias", out=ws.k)
-        ops.gemm(ws.a, sa.v.weight, sa.v.bias, "bias", out=ws.v)
-        ops.rmsnorm_rope_(ws.q, sa.norm_q.weight, sa.eps, hd, rope)
-        ops.rmsnorm_rope_(ws.k, sa.norm_k.weight, sa.eps, hd, rope)
         if sp is None:
+            ops.gemm(ws.a, sa.q.weight, sa.q.bias, "bias", out=ws.q)
+            ops.gemm(ws.a, sa.k.weight, sa.k.bias, "bias", out=ws.k)
+            ops.gemm(ws.a, sa.v.weight, sa.v.bias, "bias", out=ws.v)
+            ops.rmsnorm_rope_(ws.q, sa.norm_q.weight, sa.eps, hd, rope)
+            ops.rmsnorm_rope_(ws.k, sa.norm_k.weight, sa.eps, hd, rope)
             ops.attention(ws.q, ws.k, ws.v, n, kv_len=kv_len, out=ws.a)
         else:
-            sp.attention(ws.q, ws.k, ws.v, n, out=ws.a)
+            # K first so that its NVLink all-gather overlaps the V and Q projections, then V overlaps Q
+            ops.gemm(ws.a, sa.k.weight, sa.k.bias, "bias", out=ws.k)
+            ops.rmsnorm_rope_(ws.k, sa.norm_k.weight, sa.eps, hd, rope)
+            sp.start_gather("k", ws.k)
+            ops.gemm(ws.a, sa.v.weight, sa.v.bias, "bias", out=ws.v)
+            sp.start_gather("v", ws.v)
+            ops.gemm(ws.a, sa.q.weight, sa.q.bias, "bias", out=ws.q)
+            ops.rmsnorm_rope_(ws.q, sa.norm_q.weight, sa.eps, hd, rope)
+            sp.attention_gathered(ws.q, n, out=ws.a)
         ops.gemm(ws.a, sa.o.weight, sa.o.bias, "bias_gate_res", out=x, gate=e[2])
         # cross-attention (:504)
         if self.cross_attn_norm:
