@@ -98,3 +98,45 @@ def test_forward_rejects_cpu_and_fp32():
     m = m.to("cuda")                                      # fp32 weights: refused, not silently cast
     with pytest.raises(VcofError):
         m(x=x.cuda().bfloat16(), t=t.cuda(), context=[c.cuda().bfloat16() for c in ctx], seq_len=240)
+
+
+def test_teacache_skips_the_same_steps_as_the_reference(golden_dir):
+    """TeaCache gate (reference wan_transformer3d.py:956-1031): same skip decisions and outputs over 4 steps."""
+    from gen_golden import TEACACHE, TEACACHE_T
+    ckw, shape, n_ctx, B = DIT_CASES["dit_tiny"]
+    cfg = DiTConfig(**ckw)
+    params = make_dit_params(cfg, seed=11)
+    gold = np.load(os.path.join(golden_dir, "dit_tiny_teacache.npz"))
+    x, ctx, _ = dit_inputs(shape, n_ctx, cfg.text_dim, B, seed=23)
+    f = shape[1]
+    seq_len = f * (shape[2] // 2) * (shape[3] // 2)
+    model = build_cuda_model(cfg, params)
+    model.enable_teacache(**TEACACHE)
+    calc = []
+    for i, tv in enumerate(TEACACHE_T):
+        with torch.no_grad():
+            y = model(x=x.cuda().bfloat16(), t=torch.tensor([tv]).cuda(), context=[c.cuda().bfloat16() for c in ctx],
+                      seq_len=seq_len, **ROPE_MODES["cot"](f, B))
+        calc.append(bool(model.teacache.should_calc))
+        assert rel(y, torch.from_numpy(gold["outs"][i])) < 4e-2, (i, rel(y, torch.from_numpy(gold["outs"][i])))
+    assert calc == [bool(v) for v in gold["should_calc"]]
+    assert not all(calc), "fixture must contain at least one skipped step"
+
+
+def test_cfg_skip_drops_the_unconditional_half():
+    """cfg_skip (reference utils/cfg_optimization.py:5-38): late steps run the cond half only and duplicate it."""
+    ckw, shape, n_ctx, _ = DIT_CASES["dit_tiny"]
+    cfg = DiTConfig(**ckw)
+    params = make_dit_params(cfg, seed=11)
+    x, ctx, t = dit_inputs(shape, n_ctx, cfg.text_dim, 2, seed=23)
+    f = shape[1]
+    seq_len = f * (shape[2] // 2) * (shape[3] // 2)
+    model = build_cuda_model(cfg, params)
+    args = dict(x=x.cuda().bfloat16(), t=t.cuda(), context=[c.cuda().bfloat16() for c in ctx], seq_len=seq_len)
+    with torch.no_grad():
+        full = model(**args)
+        model.enable_cfg_skip(0.5, 4)
+        model.current_steps = 3
+        skipped = model(**args)
+    assert torch.equal(skipped[0], skipped[1])
+    assert torch.equal(skipped[1], full[1])

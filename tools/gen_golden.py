@@ -77,11 +77,42 @@ def gen_dit():
         print("wrote", name, {k: v.shape for k, v in out.items()})
 
 
+TEACACHE = dict(coefficients=[-5.21862437e+04, 9.23041404e+03, -5.28275948e+02, 1.36987616e+01, -4.99875664e-02],
+                num_steps=4, rel_l1_thresh=0.6, num_skip_start_steps=1, offload=False)
+TEACACHE_T = [999.0, 899.0, 749.0, 499.0]
+
+
+def gen_teacache():
+    """Four consecutive forwards (the 4-step schedule) with TeaCache on: records the outputs and which steps the
+    reference skipped (wan_transformer3d.py:956-1031, cache_utils.py:21-76)."""
+    from oracle.dit_oracle import DiTConfig, make_dit_params
+    ns = ref_loader.load_reference()
+    ckw, shape, n_ctx, B = DIT_CASES["dit_tiny"]
+    cfg = DiTConfig(**ckw)
+    params = make_dit_params(cfg, seed=11)
+    model = ns.dit.WanTransformer3DModel(**cfg.to_kwargs()).eval()
+    model.load_state_dict(params, strict=True)
+    model.enable_teacache(**TEACACHE)
+    x, ctx, _ = dit_inputs(shape, n_ctx, cfg.text_dim, B, seed=23)
+    f = shape[1]
+    seq_len = f * (shape[2] // 2) * (shape[3] // 2)
+    outs, calc = [], []
+    for tv in TEACACHE_T:
+        with torch.no_grad():
+            y = model(x=x, t=torch.tensor([tv]), context=ctx, seq_len=seq_len, **ROPE_MODES["cot"](f, B))
+        outs.append(y.float().numpy())
+        calc.append(bool(model.should_calc))
+    np.savez_compressed(os.path.join(GOLD, "dit_tiny_teacache.npz"), outs=np.stack(outs), should_calc=np.array(calc))
+    print("wrote dit_tiny_teacache should_calc =", calc)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     what = set(sys.argv[1:]) or {"dit", "vae", "unipc"}
     if "dit" in what:
         gen_dit()
+    if "teacache" in what or "dit" in what:
+        gen_teacache()
     if "vae" in what:
         from gen_golden_vae import gen_vae
         gen_vae()

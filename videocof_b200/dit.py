@@ -476,6 +476,28 @@ class WanTransformer3DModel(nn.Module):
             seq_len = int(math.ceil(seq_len / P)) * P                    # (:904-905)
         outs = []
         tc = self.teacache
+        embeds = [self._time_embed(t[b]) for b in range(len(xs))]
+
+        # TeaCache gate (:956-1031): ONE decision per forward, from the modulated timestep embedding of the batch
+        should_calc = True
+        if tc is not None:
+            if cond_flag:
+                mod_inp = torch.stack([e0 for _, e0 in embeds])
+                if tc.cnt < tc.num_skip_start_steps:
+                    should_calc, tc.accumulated_rel_l1_distance = True, 0
+                else:
+                    d = tc.compute_rel_l1_distance(tc.previous_modulated_input, mod_inp)
+                    tc.accumulated_rel_l1_distance += tc.rescale_func(d)
+                    if tc.accumulated_rel_l1_distance < tc.rel_l1_thresh:
+                        should_calc = False
+                    else:
+                        should_calc, tc.accumulated_rel_l1_distance = True, 0
+                tc.previous_modulated_input = mod_inp
+                tc.should_calc = should_calc
+            else:
+                should_calc = tc.should_calc
+        residuals = []
+
         for b, u in enumerate(xs):
             u = u.to(torch.bfloat16).contiguous()
             cin, F_, H_, W_ = u.shape
@@ -488,7 +510,7 @@ class WanTransformer3DModel(nn.Module):
                 torch.empty((L, C), dtype=torch.float32, device=dev)
             ops.gemm(a, self.patch_embedding.weight.view(C, -1), self.patch_embedding.bias, "bias_f32",
                      out=xb[:L])
-            e, e0 = self._time_embed(t[b])
+            e, e0 = embeds[b]
             ctx = self._text_embed(context[b])
             fs = frame_split_indices[b] if frame_split_indices is not None and b < len(frame_split_indices) else None
             gr = ground_frame_indices[b] if (fs is not None and ground_frame_indices is not None
@@ -502,26 +524,9 @@ class WanTransformer3DModel(nn.Module):
             rope = make_rope_spec(self.freqs, dev, f, h, w, fs, gr, row_offset=row0)
             mod_all = self._mod_stack() + e0                                 # [layers, 6, C] (:491)
 
-            # TeaCache gate (:956-1031)
-            should_calc = True
-            if tc is not None:
-                if cond_flag:
-                    if tc.cnt < tc.num_skip_start_steps:
-                        should_calc, tc.accumulated_rel_l1_distance = True, 0
-                    else:
-                        d = tc.compute_rel_l1_distance(tc.previous_modulated_input, e0)
-                        tc.accumulated_rel_l1_distance += tc.rescale_func(d)
-                        if tc.accumulated_rel_l1_distance < tc.rel_l1_thresh:
-                            should_calc = False
-                        else:
-                            should_calc, tc.accumulated_rel_l1_distance = True, 0
-                    tc.previous_modulated_input = e0.clone()
-                    tc.should_calc = should_calc
-                else:
-                    should_calc = tc.should_calc
             if tc is not None and not should_calc:
                 prev = tc.previous_residual_cond if cond_flag else tc.previous_residual_uncond
-                xb = xb + prev.to(dev)
+                xb = xb + prev[b - len(xs)].to(dev)                          # `[-x.size(0):]` of the stored batch
             else:
                 ori = xb.clone() if tc is not None else None
                 ws = self._ws.get(dev, rows, C, self.ffn_dim)
@@ -529,11 +534,7 @@ class WanTransformer3DModel(nn.Module):
                     blk.run(xb, mod_all[i], ctx, rope, L, ws, sp if P > 1 else None)
                 if tc is not None:
                     res = xb - ori
-                    res = res.cpu() if tc.offload else res
-                    if cond_flag:
-                        tc.previous_residual_cond = res
-                    else:
-                        tc.previous_residual_uncond = res
+                    residuals.append(res.cpu() if tc.offload else res)
 
             # head (:535-548) — modulation uses e, not e0
             eh = (self.head.modulation.detach().to(torch.float32)[0] + e).contiguous()   # [2, C]
@@ -542,6 +543,12 @@ class WanTransformer3DModel(nn.Module):
             if P > 1:
                 yo = sp.all_gather_rows(yo)                                                   # (:1085-1086)
             outs.append(ops.unpatchify(yo[:L], self.out_dim, f, H_, W_))                     # (:1108-1131)
+        if tc is not None and residuals:
+            stacked = torch.stack(residuals)
+            if cond_flag:
+                tc.previous_residual_cond = stacked
+            else:
+                tc.previous_residual_uncond = stacked
         if tc is not None and cond_flag:
             tc.cnt += 1
             if tc.cnt == tc.num_steps:
