@@ -433,12 +433,14 @@ extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long l
   const int items = a.heads * a.num_q_blocks;
   const int grid = items < sm_count() ? items : sm_count();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // fraction of exponentials evaluated on the FMA pipe; VCOF_ATTN_EMU=0..4 overrides (tuning knob)
+  // Fraction (of 8) of exponentials evaluated on the FMA pipe; VCOF_ATTN_EMU=0|2|3|4 overrides.  Measured on
+  // B200 (profiles/r1_gpurun6_emu_sweep_vae_bench.log, L=75600, 8 heads): 0 -> 17.14 ms, 2 -> 17.55, 3 -> 18.02,
+  // 4 -> 18.46: the FMA/ALU issue slots, not MUFU, are the scarcer resource here, so the default is 0.
   static int emu = -1;
   if (emu < 0) {
     const char* e = getenv("VCOF_ATTN_EMU");
-    emu = e ? atoi(e) : 3;
-    if (emu < 0 || emu > 4) emu = 3;
+    emu = e ? atoi(e) : 0;
+    if (emu < 0 || emu > 4) emu = 0;
   }
   auto launch = [&](auto kern) -> int {
     VCOF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
@@ -448,17 +450,17 @@ extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long l
   int lrc = 0;
   if (v_transposed) {
     switch (emu) {
-      case 0: lrc = launch(attn_fwd_kernel<true, 0>); break;
       case 2: lrc = launch(attn_fwd_kernel<true, 2>); break;
+      case 3: lrc = launch(attn_fwd_kernel<true, 3>); break;
       case 4: lrc = launch(attn_fwd_kernel<true, 4>); break;
-      default: lrc = launch(attn_fwd_kernel<true, 3>); break;
+      default: lrc = launch(attn_fwd_kernel<true, 0>); break;
     }
   } else {
     switch (emu) {
-      case 0: lrc = launch(attn_fwd_kernel<false, 0>); break;
       case 2: lrc = launch(attn_fwd_kernel<false, 2>); break;
+      case 3: lrc = launch(attn_fwd_kernel<false, 3>); break;
       case 4: lrc = launch(attn_fwd_kernel<false, 4>); break;
-      default: lrc = launch(attn_fwd_kernel<false, 3>); break;
+      default: lrc = launch(attn_fwd_kernel<false, 0>); break;
     }
   }
   if (lrc) return lrc;
