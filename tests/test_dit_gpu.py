@@ -117,7 +117,7 @@ def test_teacache_skips_the_same_steps_as_the_reference(golden_dir):
         with torch.no_grad():
             y = model(x=x.cuda().bfloat16(), t=torch.tensor([tv]).cuda(), context=[c.cuda().bfloat16() for c in ctx],
                       seq_len=seq_len, **ROPE_MODES["cot"](f, B))
-        calc.append(bool(model.teacache.should_calc))
+        calc.append(bool(model.should_calc))
         assert rel(y, torch.from_numpy(gold["outs"][i])) < 4e-2, (i, rel(y, torch.from_numpy(gold["outs"][i])))
     assert calc == [bool(v) for v in gold["should_calc"]]
     assert not all(calc), "fixture must contain at least one skipped step"

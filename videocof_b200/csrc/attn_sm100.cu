@@ -74,7 +74,9 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 }
 
 // EMU: of every 8 element pairs, this many take the polynomial path (0 = all MUFU).
-template <bool V_TRANS, int EMU>
+// SPLIT_S: S_t = Q_t K_j^T is issued as two N=64 halves with separate barriers, so the softmax warps load and
+// reduce the first 64 score columns while the tensor pipe still computes the second half.
+template <bool V_TRANS, int EMU, bool SPLIT_S>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
@@ -90,8 +92,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t q_full = b0, q_empty = b0 + 16;
   const uint32_t k_full = b0 + 32, k_empty = b0 + 48;
   const uint32_t v_full = b0 + 64, v_empty = b0 + 80;
-  const uint32_t s_full = b0 + 96, p_full = b0 + 112, o_full = b0 + 128;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  const uint32_t s_full = b0 + 96, p_full = b0 + 112, o_full = b0 + 128, p_full2 = b0 + 144;
+  const uint32_t s_full2 = b0 + 160;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -111,6 +114,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(v_empty + 8 * i, 1);
       mbar_init(s_full + 8 * i, 1);
       mbar_init(p_full + 8 * i, 4);
+      mbar_init(p_full2 + 8 * i, 4);
+      mbar_init(s_full2 + 8 * i, 1);
       mbar_init(o_full + 8 * i, 1);
     }
     fence_barrier_init();
@@ -127,7 +132,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // Register re-balancing between warpgroups: the softmax threads keep a whole 128-wide
   // score row live, the producer / MMA warpgroup needs almost nothing.
   if (warp >= 8) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
    if (warp == 8) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
@@ -189,27 +194,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t tS[2] = {tmem_base, tmem_base + 128};
       const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
 
+      constexpr uint32_t idesc_qk64 = make_idesc_bf16(kQT, 64, false, false);
+      // S_t = Q_t K^T, committed to s_full (and, when split, first to s_full for columns 0..63 then to
+      // s_full2 for columns 64..127)
       auto mma_s = [&](int t, int kstage) {
-        const uint32_t a = smem_u32(sQ + t * kTile);
-        const uint32_t b = smem_u32(sK + kstage * kTile);
+        // descriptors differ only in the 14-bit start-address field: build once, add (byte offset >> 4)
+        const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sQ + t * kTile));
+        const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sK + kstage * kTile));
+        if (SPLIT_S) {
 #pragma unroll
-        for (int k = 0; k < kHD / 16; ++k) {
-          const uint32_t off = (k >> 2) * kHalf + (k & 3) * 32;
-          umma_ss(tS[t], make_desc_kmajor_sw128(a + off), make_desc_kmajor_sw128(b + off),
-                  idesc_qk, k != 0);
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int k = 0; k < kHD / 16; ++k) {
+              const uint32_t off = ((k >> 2) * kHalf + (k & 3) * 32) >> 4;
+              umma_ss(tS[t] + half * 64, ad + off, bd + off + ((half * 64 * 128) >> 4), idesc_qk64, k != 0);
+            }
+            umma_commit((half == 0 ? s_full : s_full2) + 8 * t);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kHD / 16; ++k) {
+            const uint32_t off = ((k >> 2) * kHalf + (k & 3) * 32) >> 4;
+            umma_ss(tS[t], ad + off, bd + off, idesc_qk, k != 0);
+          }
+          umma_commit(s_full + 8 * t);
         }
       };
-      auto mma_pv = [&](int t, int vstage, bool first) {
+      // PV in two K-halves: the first half (kv rows 0..63) is issued as soon as the softmax warps have
+      // published P[:, 0:64], overlapping the exponentials of the second half.
+      auto mma_pv = [&](int t, int vstage, bool first, int half) {
         const uint32_t b = smem_u32(sV + vstage * kTile);
+        const uint64_t bd0 = V_TRANS ? make_desc_kmajor_sw128(b) : make_desc_mnmajor_sw128(b, kHalf, 1024);
 #pragma unroll
-        for (int k = 0; k < kKT / 16; ++k) {
-          uint64_t bd;
-          if (V_TRANS) {
-            bd = make_desc_kmajor_sw128(b + (k >> 2) * kHalf + (k & 3) * 32);
-          } else {
-            bd = make_desc_mnmajor_sw128(b + k * 16 * 128, kHalf, 1024);
-          }
-          umma_ts(tO[t], tS[t] + k * 8, bd, idesc_pv, (!first || k != 0));
+        for (int kk = 0; kk < kKT / 32; ++kk) {
+          const int k = half * (kKT / 32) + kk;
+          const uint32_t off = V_TRANS ? (((k >> 2) * kHalf + (k & 3) * 32) >> 4) : ((k * 16 * 128) >> 4);
+          umma_ts(tO[t], tS[t] + k * 8, bd0 + off, idesc_pv, (!first || k != 0));
         }
       };
 
@@ -219,12 +239,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(k_full + 8 * ks, kph);
         tc_fence_after();
         mma_s(0, ks);
-        umma_commit(s_full + 0);
         if (n_kv == 1) umma_commit(q_empty + 0);
         mbar_wait(q_full + 8, item_ph);
         tc_fence_after();
         mma_s(1, ks);
-        umma_commit(s_full + 8);
         if (n_kv == 1) umma_commit(q_empty + 8);
         umma_commit(k_empty + 8 * ks);
         if (++ks == kKVStages) { ks = 0; kph ^= 1; }
@@ -234,28 +252,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           // ---- tile 0: O0 += P0(j) V_j ; then S0(j+1)
           mbar_wait(v_full + 8 * vs, vph);
           mbar_wait(p_full + 0, pph[0]);
+          tc_fence_after();
+          mma_pv(0, vs, j == 0, 0);
+          mbar_wait(p_full2 + 0, pph[0]);
           pph[0] ^= 1;
           tc_fence_after();
-          mma_pv(0, vs, j == 0);
+          mma_pv(0, vs, j == 0, 1);
           if (!last) {
             mbar_wait(k_full + 8 * ks, kph);
             tc_fence_after();
             mma_s(0, ks);
-            umma_commit(s_full + 0);
             if (j + 2 == n_kv) umma_commit(q_empty + 0);
           } else {
             umma_commit(o_full + 0);
           }
           // ---- tile 1: O1 += P1(j) V_j ; then S1(j+1)
           mbar_wait(p_full + 8, pph[1]);
+          tc_fence_after();
+          mma_pv(1, vs, j == 0, 0);
+          mbar_wait(p_full2 + 8, pph[1]);
           pph[1] ^= 1;
           tc_fence_after();
-          mma_pv(1, vs, j == 0);
+          mma_pv(1, vs, j == 0, 1);
           umma_commit(v_empty + 8 * vs);
           if (++vs == kKVStages) { vs = 0; vph ^= 1; }
           if (!last) {
             mma_s(1, ks);
-            umma_commit(s_full + 8);
             if (j + 2 == n_kv) umma_commit(q_empty + 8);
             umma_commit(k_empty + 8 * ks);
             if (++ks == kKVStages) { ks = 0; kph ^= 1; }
@@ -267,7 +289,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
    }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     // =========================== softmax + epilogue ===========================
     const int t = warp >> 2;                         // which Q tile
     const uint32_t lane_base = ((warp & 3) * 32u) << 16;
@@ -283,12 +305,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float m_ref = -INFINITY;  // running (possibly stale) row max, raw score units
       float l = 0.f;
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(s_full + 8 * t, sph);
-        sph ^= 1;
-        tc_fence_after();
         uint32_t s[128];
+        mbar_wait(s_full + 8 * t, sph);
+        tc_fence_after();
         tmem_ld32(tS + 0, s + 0);
         tmem_ld32(tS + 32, s + 32);
+        if (SPLIT_S) {
+          mbar_wait(s_full2 + 8 * t, sph);
+          tc_fence_after();
+        }
+        sph ^= 1;
         tmem_ld32(tS + 64, s + 64);
         tmem_ld32(tS + 96, s + 96);
         tmem_ld_wait();
@@ -350,13 +376,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             pk[c] = pack_bf16x2(pr.x, pr.y);
           }
           tmem_st32(tS + h * 32, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive((h == 0 ? p_full : p_full2) + 8 * t);
         }
         const float l0 = acc0.x + acc1.x, l1 = acc0.y + acc1.y, l2 = 0.f, l3 = 0.f;
         l += (l0 + l1) + (l2 + l3);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full + 8 * t);
       }
       // ---- epilogue: O_t / l -> bf16 -> global
       mbar_wait(o_full + 8 * t, oph);
@@ -433,35 +459,36 @@ extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long l
   const int items = a.heads * a.num_q_blocks;
   const int grid = items < sm_count() ? items : sm_count();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // Fraction (of 8) of exponentials evaluated on the FMA pipe; VCOF_ATTN_EMU=0|2|3|4 overrides.  Measured on
+  // Fraction (of 8) of exponentials evaluated on the FMA pipe; VCOF_ATTN_EMU=0|3 overrides.  Measured on
   // B200 (profiles/r1_gpurun6_emu_sweep_vae_bench.log, L=75600, 8 heads): 0 -> 17.14 ms, 2 -> 17.55, 3 -> 18.02,
   // 4 -> 18.46: the FMA/ALU issue slots, not MUFU, are the scarcer resource here, so the default is 0.
   static int emu = -1;
   if (emu < 0) {
     const char* e = getenv("VCOF_ATTN_EMU");
     emu = e ? atoi(e) : 0;
-    if (emu < 0 || emu > 4) emu = 0;
+    if (emu != 3) emu = 0;
   }
   auto launch = [&](auto kern) -> int {
     VCOF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     kern<<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, a);
     return 0;
   };
+  static int split_s = -1;
+  if (split_s < 0) {
+    const char* e = getenv("VCOF_ATTN_SPLIT_S");
+    split_s = e ? (atoi(e) != 0) : 1;
+  }
   int lrc = 0;
-  if (v_transposed) {
-    switch (emu) {
-      case 2: lrc = launch(attn_fwd_kernel<true, 2>); break;
-      case 3: lrc = launch(attn_fwd_kernel<true, 3>); break;
-      case 4: lrc = launch(attn_fwd_kernel<true, 4>); break;
-      default: lrc = launch(attn_fwd_kernel<true, 0>); break;
-    }
-  } else {
-    switch (emu) {
-      case 2: lrc = launch(attn_fwd_kernel<false, 2>); break;
-      case 3: lrc = launch(attn_fwd_kernel<false, 3>); break;
-      case 4: lrc = launch(attn_fwd_kernel<false, 4>); break;
-      default: lrc = launch(attn_fwd_kernel<false, 0>); break;
-    }
+  const int variant = (v_transposed ? 4 : 0) + (emu == 3 ? 2 : 0) + (split_s ? 1 : 0);
+  switch (variant) {
+    case 0: lrc = launch(attn_fwd_kernel<false, 0, false>); break;
+    case 1: lrc = launch(attn_fwd_kernel<false, 0, true>); break;
+    case 2: lrc = launch(attn_fwd_kernel<false, 3, false>); break;
+    case 3: lrc = launch(attn_fwd_kernel<false, 3, true>); break;
+    case 4: lrc = launch(attn_fwd_kernel<true, 0, false>); break;
+    case 5: lrc = launch(attn_fwd_kernel<true, 0, true>); break;
+    case 6: lrc = launch(attn_fwd_kernel<true, 3, false>); break;
+    default: lrc = launch(attn_fwd_kernel<true, 3, true>); break;
   }
   if (lrc) return lrc;
   VCOF_CHECK_CUDA(cudaGetLastError());

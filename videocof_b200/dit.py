@@ -496,6 +496,7 @@ class WanTransformer3DModel(nn.Module):
                 tc.should_calc = should_calc
             else:
                 should_calc = tc.should_calc
+            self.should_calc = should_calc          # attribute the reference also exposes (:968-981)
         residuals = []
 
         for b, u in enumerate(xs):
