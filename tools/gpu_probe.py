@@ -37,6 +37,9 @@ def cases():
                 continue
             cs.append(dict(kind="attn", Lq=Lq, Lk=Lk, kv=kv, heads=h, vt=vt))
     cs.append(dict(kind="attn", Lq=1024, Lk=4096, kv=4096, heads=2, vt=0, big_scores=1))
+    # > 148 work items: persistent CTAs walk several (head, q-block) items (barrier phases across items)
+    cs.append(dict(kind="attn", Lq=4096, Lk=4000, kv=3999, heads=12, vt=0))
+    cs.append(dict(kind="attn", Lq=9000, Lk=1111, kv=1111, heads=10, vt=0))
     for (L, C) in [(64, 1536), (1000, 5120), (333, 2048)]:
         for mode in ("plain", "mod", "affine"):
             cs.append(dict(kind="ln", L=L, C=C, mode=mode))
