@@ -76,7 +76,8 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // EMU: of every 8 element pairs, this many take the polynomial path (0 = all MUFU).
 // SPLIT_S: S_t = Q_t K_j^T is issued as two N=64 halves with separate barriers, so the softmax warps load and
 // reduce the first 64 score columns while the tensor pipe still computes the second half.
-template <bool V_TRANS, int EMU, bool SPLIT_S>
+// PSPLIT: number of K-chunks (2 or 4) in which P is published to the PV MMA.
+template <bool V_TRANS, int EMU, bool SPLIT_S, int PSPLIT>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
@@ -94,7 +95,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t v_full = b0 + 64, v_empty = b0 + 80;
   const uint32_t s_full = b0 + 96, p_full = b0 + 112, o_full = b0 + 128, p_full2 = b0 + 144;
   const uint32_t s_full2 = b0 + 160;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  const uint32_t p_part = b0 + 176;   // [PSPLIT][2 tiles]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -116,6 +118,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(p_full + 8 * i, 4);
       mbar_init(p_full2 + 8 * i, 4);
       mbar_init(s_full2 + 8 * i, 1);
+      for (int q = 0; q < 4; ++q) mbar_init(p_part + 8 * (q * 2 + i), 4);
       mbar_init(o_full + 8 * i, 1);
     }
     fence_barrier_init();
@@ -132,7 +135,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // Register re-balancing between warpgroups: the softmax threads keep a whole 128-wide
   // score row live, the producer / MMA warpgroup needs almost nothing.
   if (warp >= 8) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
    if (warp == 8) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
@@ -222,14 +225,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       };
       // PV in two K-halves: the first half (kv rows 0..63) is issued as soon as the softmax warps have
       // published P[:, 0:64], overlapping the exponentials of the second half.
-      auto mma_pv = [&](int t, int vstage, bool first, int half) {
+      auto mma_pv = [&](int t, int vstage, bool first, uint32_t parity) {
         const uint32_t b = smem_u32(sV + vstage * kTile);
         const uint64_t bd0 = V_TRANS ? make_desc_kmajor_sw128(b) : make_desc_mnmajor_sw128(b, kHalf, 1024);
 #pragma unroll
-        for (int kk = 0; kk < kKT / 32; ++kk) {
-          const int k = half * (kKT / 32) + kk;
-          const uint32_t off = V_TRANS ? (((k >> 2) * kHalf + (k & 3) * 32) >> 4) : ((k * 16 * 128) >> 4);
-          umma_ts(tO[t], tS[t] + k * 8, bd0 + off, idesc_pv, (!first || k != 0));
+        for (int part = 0; part < PSPLIT; ++part) {
+          mbar_wait(p_part + 8 * (part * 2 + t), parity);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < kKT / 16 / PSPLIT; ++kk) {
+            const int k = part * (kKT / 16 / PSPLIT) + kk;
+            const uint32_t off = V_TRANS ? (((k >> 2) * kHalf + (k & 3) * 32) >> 4) : ((k * 16 * 128) >> 4);
+            umma_ts(tO[t], tS[t] + k * 8, bd0 + off, idesc_pv, (!first || k != 0));
+          }
         }
       };
 
@@ -251,13 +259,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const bool last = (j + 1 == n_kv);
           // ---- tile 0: O0 += P0(j) V_j ; then S0(j+1)
           mbar_wait(v_full + 8 * vs, vph);
-          mbar_wait(p_full + 0, pph[0]);
-          tc_fence_after();
-          mma_pv(0, vs, j == 0, 0);
-          mbar_wait(p_full2 + 0, pph[0]);
+          mma_pv(0, vs, j == 0, pph[0]);
           pph[0] ^= 1;
-          tc_fence_after();
-          mma_pv(0, vs, j == 0, 1);
           if (!last) {
             mbar_wait(k_full + 8 * ks, kph);
             tc_fence_after();
@@ -267,13 +270,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_commit(o_full + 0);
           }
           // ---- tile 1: O1 += P1(j) V_j ; then S1(j+1)
-          mbar_wait(p_full + 8, pph[1]);
-          tc_fence_after();
-          mma_pv(1, vs, j == 0, 0);
-          mbar_wait(p_full2 + 8, pph[1]);
+          mma_pv(1, vs, j == 0, pph[1]);
           pph[1] ^= 1;
-          tc_fence_after();
-          mma_pv(1, vs, j == 0, 1);
           umma_commit(v_empty + 8 * vs);
           if (++vs == kKVStages) { vs = 0; vph ^= 1; }
           if (!last) {
@@ -289,7 +287,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
    }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // =========================== softmax + epilogue ===========================
     const int t = warp >> 2;                         // which Q tile
     const uint32_t lane_base = ((warp & 3) * 32u) << 16;
@@ -358,11 +356,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float2 nmb2 = make_float2(-mb, -mb);
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t pk[32];
+        for (int h = 0; h < PSPLIT; ++h) {
+          constexpr int kPairs = 64 / PSPLIT;          // packed bf16x2 columns per part
+          uint32_t pk[kPairs];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int e0 = h * 64 + 2 * c;
+          for (int c = 0; c < kPairs; ++c) {
+            const int e0 = h * (128 / PSPLIT) + 2 * c;
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e0]), __uint_as_float(s[e0 + 1])),
                                         sc2, nmb2);
             float2 pr;
@@ -375,11 +374,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (c & 1) acc1 = __fadd2_rn(acc1, pr); else acc0 = __fadd2_rn(acc0, pr);
             pk[c] = pack_bf16x2(pr.x, pr.y);
           }
-          tmem_st32(tS + h * 32, pk);
+          if (PSPLIT == 2) tmem_st32(tS + h * kPairs, pk); else tmem_st16(tS + h * kPairs, pk);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive((h == 0 ? p_full : p_full2) + 8 * t);
+          if (lane == 0) mbar_arrive(p_part + 8 * (h * 2 + t));
         }
         const float l0 = acc0.x + acc1.x, l1 = acc0.y + acc1.y, l2 = 0.f, l3 = 0.f;
         l += (l0 + l1) + (l2 + l3);
@@ -473,22 +472,23 @@ extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long l
     kern<<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, a);
     return 0;
   };
-  static int split_s = -1;
+  // VCOF_ATTN_SPLIT_S=1 / VCOF_ATTN_PSPLIT=2|4: tuning knobs (measured defaults: profiles/README.md)
+  static int split_s = -1, psplit = -1;
   if (split_s < 0) {
     const char* e = getenv("VCOF_ATTN_SPLIT_S");
-    split_s = e ? (atoi(e) != 0) : 1;
+    split_s = e ? (atoi(e) != 0) : 0;
+    const char* q = getenv("VCOF_ATTN_PSPLIT");
+    psplit = (q && atoi(q) == 4) ? 4 : 2;
   }
   int lrc = 0;
-  const int variant = (v_transposed ? 4 : 0) + (emu == 3 ? 2 : 0) + (split_s ? 1 : 0);
-  switch (variant) {
-    case 0: lrc = launch(attn_fwd_kernel<false, 0, false>); break;
-    case 1: lrc = launch(attn_fwd_kernel<false, 0, true>); break;
-    case 2: lrc = launch(attn_fwd_kernel<false, 3, false>); break;
-    case 3: lrc = launch(attn_fwd_kernel<false, 3, true>); break;
-    case 4: lrc = launch(attn_fwd_kernel<true, 0, false>); break;
-    case 5: lrc = launch(attn_fwd_kernel<true, 0, true>); break;
-    case 6: lrc = launch(attn_fwd_kernel<true, 3, false>); break;
-    default: lrc = launch(attn_fwd_kernel<true, 3, true>); break;
+  if (emu == 3 || split_s) {            // experimental variants, natural-V layout only
+    VCOF_REQUIRE(!v_transposed, "vcof_attn_fwd: tuning variants support the natural V layout only");
+    if (emu == 3) lrc = launch(attn_fwd_kernel<false, 3, false, 2>);
+    else lrc = launch(attn_fwd_kernel<false, 0, true, 2>);
+  } else if (v_transposed) {
+    lrc = psplit == 4 ? launch(attn_fwd_kernel<true, 0, false, 4>) : launch(attn_fwd_kernel<true, 0, false, 2>);
+  } else {
+    lrc = psplit == 4 ? launch(attn_fwd_kernel<false, 0, false, 4>) : launch(attn_fwd_kernel<false, 0, false, 2>);
   }
   if (lrc) return lrc;
   VCOF_CHECK_CUDA(cudaGetLastError());
