@@ -22,11 +22,10 @@
 namespace vcof {
 
 constexpr int kCvThreads = 192;
-constexpr int kCvStages = 6;
+constexpr int kCvMaxStages = 16;             // ring depth is chosen at launch: smem / (A + B bytes of this conv)
 constexpr int kCvABytes = 128 * 64;          // 128 positions x 32 channels bf16
-constexpr int kCvBBytesMax = 384 * 64;       // up to 384 output channels x 32 k
-constexpr int kCvStage = kCvABytes + kCvBBytesMax;
-constexpr int kCvSmem = kCvStages * kCvStage + 256 + 1024;
+constexpr int kCvData = 200 * 1024;          // operand ring budget
+constexpr int kCvSmem = kCvData + 512 + 1024;
 constexpr int kMaxTaps = 27;
 
 constexpr uint64_t kDescSwizzle64 = 4ull << 61;
@@ -54,6 +53,7 @@ struct ConvArgs {
   long long ldc;
   int interleave_half;        // > 0: channels >= this go to frame+1 and are stored at (n - half)
   int n_store;                // channels actually stored per position (<= n_total)
+  int stages, stage_bytes;    // TMA ring: deep enough to cover L2 latency at ~150 B/clk/SM (small-N convs)
   const float* bias;          // [n_total] fp32 or nullptr
   const bf16* residual;       // same addressing as out, or nullptr
   bf16* out;                  // raw output, may be nullptr when only act_out is wanted
@@ -68,12 +68,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCvStages * kCvStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCvData);
   const uint32_t bar_full = smem_u32(bars);
-  const uint32_t bar_empty = bar_full + 8 * kCvStages;
-  const uint32_t bar_tfull = bar_empty + 8 * kCvStages;
+  const uint32_t bar_empty = bar_full + 8 * kCvMaxStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kCvMaxStages;
   const uint32_t bar_tempty = bar_tfull + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kCvStages + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kCvMaxStages + 4);
+  const int kCvStages = p.stages;
+  const int kCvStage = p.stage_bytes;
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -83,7 +85,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
   if (warp == 5) {
     if (lane == 0) {
-      for (int i = 0; i < kCvStages; ++i) {
+      for (int i = 0; i < kCvMaxStages; ++i) {
         mbar_init(bar_full + 8 * i, 1);
         mbar_init(bar_empty + 8 * i, 1);
       }
@@ -452,6 +454,9 @@ extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const lon
                "vcof_conv_igemm: n_total %d / n_tile %d must be multiples of 16, n_tile <= 384", a.n_total,
                a.n_tile);
   VCOF_REQUIRE(a.n_tile <= 256 || (a.n_tile / 2) % 16 == 0, "vcof_conv_igemm: n_tile/2 must be a multiple of 16");
+  a.stage_bytes = (kCvABytes + a.n_tile * 64 + 1023) / 1024 * 1024;
+  a.stages = kCvData / a.stage_bytes;
+  if (a.stages > kCvMaxStages) a.stages = kCvMaxStages;
   VCOF_REQUIRE(k_total == ntaps * cin, "vcof_conv_igemm: weight K %d != ntaps*cin %d", k_total, ntaps * cin);
   VCOF_REQUIRE(ldc % 8 == 0, "vcof_conv_igemm: ldc must be a multiple of 8");
   CUtensorMap tmX, tmW;
