@@ -53,7 +53,9 @@ struct ConvArgs {
   long long ldc;
   int interleave_half;        // > 0: channels >= this go to frame+1 and are stored at (n - half)
   int n_store;                // channels actually stored per position (<= n_total)
-  int stages, stage_bytes;    // TMA ring: deep enough to cover L2 latency at ~150 B/clk/SM (small-N convs)
+  int stages, stage_bytes;    // TMA ring geometry chosen at launch
+  int group;                  // 32-channel slices per ring stage (1..3): one mbarrier round-trip then covers
+                              // >= ~300 MMA cycles even for N = 96, so the single MMA-issuing thread keeps up
   const float* bias;          // [n_total] fp32 or nullptr
   const bf16* residual;       // same addressing as out, or nullptr
   bf16* out;                  // raw output, may be nullptr when only act_out is wanted
@@ -106,7 +108,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int tiles_w = (p.W_out + 15) / 16, tiles_h = (p.H_out + 7) / 8;
   const int n_tiles = (p.n_total + p.n_tile - 1) / p.n_tile;
   const int num_tiles = p.T_out * tiles_h * tiles_w * n_tiles;
-  const int num_k = p.ntaps * p.cin_chunks;
+  const int num_k = p.ntaps * (p.cin_chunks / p.group);
   const int nacc = (p.n_tile <= 256) ? 2 : 1;            // accumulator buffers in TMEM
   const int nsub = (p.n_tile <= 256) ? 1 : 2;            // MMAs per k-step (N <= 256 each)
   const int n_sub = p.n_tile / nsub;
@@ -131,16 +133,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         decode(tile, t, h0, w0, n0);
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const ConvTap tp = p.taps[tap];
-          for (int cc = 0; cc < p.cin_chunks; ++cc) {
+          for (int cc = 0; cc < p.cin_chunks; cc += p.group) {
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            mbar_expect_tx(bar_full + 8 * s, kCvABytes + b_bytes);
+            mbar_expect_tx(bar_full + 8 * s, p.group * (kCvABytes + b_bytes));
             uint8_t* st = smem + s * kCvStage;
-            tma_load_5d(smem_u32(st), &tmX, bar_full + 8 * s, tp.c_base + cc * 32, w0 + tp.dw, tp.p,
-                        h0 + tp.dh, t * p.t_stride + tp.dt);
-            const int kk = tap * p.cin + cc * 32;
-            for (int j = 0; j < nsub; ++j)
-              tma_load_2d(smem_u32(st + kCvABytes + j * n_sub * 64), &tmW, bar_full + 8 * s, kk,
-                          n0 + j * n_sub);
+            for (int g = 0; g < p.group; ++g) {
+              uint8_t* sg = st + g * (kCvABytes + b_bytes);
+              tma_load_5d(smem_u32(sg), &tmX, bar_full + 8 * s, tp.c_base + (cc + g) * 32, w0 + tp.dw, tp.p,
+                          h0 + tp.dh, t * p.t_stride + tp.dt);
+              const int kk = tap * p.cin + (cc + g) * 32;
+              for (int j = 0; j < nsub; ++j)
+                tma_load_2d(smem_u32(sg + kCvABytes + j * n_sub * 64), &tmW, bar_full + 8 * s, kk,
+                            n0 + j * n_sub);
+            }
             if (++s == kCvStages) { s = 0; ph ^= 1; }
           }
         }
@@ -161,13 +166,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int k = 0; k < num_k; ++k) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + s * kCvStage);
-          const uint32_t b_base = a_base + kCvABytes;
+          for (int g = 0; g < p.group; ++g) {
+            const uint32_t a_base = smem_u32(smem + s * kCvStage) + g * (kCvABytes + b_bytes);
+            const uint32_t b_base = a_base + kCvABytes;
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            for (int j = 0; j < nsub; ++j)
-              umma_ss(d_tmem + j * n_sub, make_desc_kmajor_sw64(a_base + ks * 32),
-                      make_desc_kmajor_sw64(b_base + j * n_sub * 64 + ks * 32), idesc, (k | ks) != 0);
+            for (int ks = 0; ks < 2; ++ks) {
+              for (int j = 0; j < nsub; ++j)
+                umma_ss(d_tmem + j * n_sub, make_desc_kmajor_sw64(a_base + ks * 32),
+                        make_desc_kmajor_sw64(b_base + j * n_sub * 64 + ks * 32), idesc, (k | g | ks) != 0);
+            }
           }
           umma_commit(bar_empty + 8 * s);
           if (++s == kCvStages) { s = 0; ph ^= 1; }
@@ -454,7 +461,9 @@ extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const lon
                "vcof_conv_igemm: n_total %d / n_tile %d must be multiples of 16, n_tile <= 384", a.n_total,
                a.n_tile);
   VCOF_REQUIRE(a.n_tile <= 256 || (a.n_tile / 2) % 16 == 0, "vcof_conv_igemm: n_tile/2 must be a multiple of 16");
-  a.stage_bytes = (kCvABytes + a.n_tile * 64 + 1023) / 1024 * 1024;
+  a.group = a.n_tile <= 128 ? 3 : (a.n_tile <= 256 ? 2 : 1);
+  while (a.cin_chunks % a.group) --a.group;
+  a.stage_bytes = a.group * (kCvABytes + a.n_tile * 64);     // multiples of 512 B keep SW64 tiles aligned
   a.stages = kCvData / a.stage_bytes;
   if (a.stages > kCvMaxStages) a.stages = kCvMaxStages;
   VCOF_REQUIRE(k_total == ntaps * cin, "vcof_conv_igemm: weight K %d != ntaps*cin %d", k_total, ntaps * cin);

@@ -235,6 +235,68 @@ def _bf(mod, name, t):
 
 
 # ----------------------------------------------------------------------------------------------
+# temporal sharding (multi-GPU): contiguous frame ranges per rank, 2-frame halos per causal convolution
+# ----------------------------------------------------------------------------------------------
+class TimeShard:
+    """Temporal sharding context of one VAE call.
+
+    Rank r owns a contiguous range of frames at every level of the network (latent frame i > 0 maps to 2 frames
+    after each temporal up-sampler, so ownership stays aligned to latent frames).  Every activation tensor is
+    allocated with HALO leading frames; a causal (k_t = 3) convolution first receives the last two frames of its
+    input from rank r-1 into that halo (rank 0 keeps zeros = the causal padding, reference wan_vae.py:26-40) and
+    then runs the ordinary TMA-tiled kernel on the haloed view.  New design: the reference has no VAE
+    parallelism in-tree (the hook is the proprietary paifuser.parallel_magvit_vae)."""
+    HALO = 2
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+
+    def exchange(self, xh, send=None):
+        """xh: haloed buffer [HALO + T, H, W, C]; fills xh[:HALO] with the left neighbour's last HALO frames
+        (`send` overrides what this rank ships to the right, default xh[-HALO:])."""
+        dist = self.dist
+        ops_ = []
+        if self.rank > 0:
+            recv = torch.empty_like(xh[:self.HALO])
+            ops_.append(dist.P2POp(dist.irecv, recv, dist.get_global_rank(self.group, self.rank - 1), self.group))
+        else:
+            xh[:self.HALO].zero_()
+        if self.rank + 1 < self.world:
+            out = (xh[-self.HALO:] if send is None else send).contiguous()
+            ops_.append(dist.P2POp(dist.isend, out, dist.get_global_rank(self.group, self.rank + 1), self.group))
+        if ops_:
+            for w in dist.batch_isend_irecv(ops_):
+                w.wait()
+        if self.rank > 0:
+            xh[:self.HALO].copy_(recv)
+
+
+_SHARD = None      # active TimeShard of the current encode/decode call (None = single GPU)
+
+
+def _alloc(T, H, W, C, device, zero=False):
+    """Channels-last activation [T, H, W, C]; under temporal sharding it is the tail of a buffer that carries
+    TimeShard.HALO extra leading frames (see _haloed)."""
+    extra = TimeShard.HALO if _SHARD is not None else 0
+    mk = torch.zeros if zero else torch.empty
+    buf = mk((T + extra, H, W, C), dtype=torch.bfloat16, device=device)
+    return buf[extra:]
+
+
+def _haloed(x):
+    """Zero-copy view [HALO + T, H, W, C] of a tensor made by _alloc."""
+    h = TimeShard.HALO
+    off = x.storage_offset() - h * x.stride(0)
+    if off < 0:
+        raise VcofError("activation was not allocated with a temporal halo")
+    return x.as_strided((x.shape[0] + h,) + tuple(x.shape[1:]), x.stride(), off)
+
+
+# ----------------------------------------------------------------------------------------------
 # channels-last building blocks: x is bf16 [T, H, W, C] contiguous
 # ----------------------------------------------------------------------------------------------
 def _geom(T, H, W, n_total, n_tile, ot=(1, 0), oh=(1, 0), ow=(1, 0), Hs=None, Ws=None, t_stride=1, half=0,
@@ -264,22 +326,29 @@ def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None, act_norm=None, 
         raise VcofError(f"conv input has {C} channels, packed weight expects {cin_p}")
     k = conv.kernel_size
     kt, kh, kw = (1, k[0], k[1]) if len(k) == 2 else k
-    taps = [(0, j - kw // 2, 0, i - kh // 2, a - (kt - 1)) for a in range(kt) for i in range(kh) for j in range(kw)]
+    t_shift = 0
+    xin = x
+    if _SHARD is not None and kt > 1:
+        # temporal sharding: pull the two preceding frames from the left neighbour into the halo, then index time
+        # from the start of the haloed buffer (no negative coordinates: rank 0's halo is the causal zero padding)
+        xin = _haloed(x)
+        _SHARD.exchange(xin)
+        t_shift = TimeShard.HALO
+    taps = [(0, j - kw // 2, 0, i - kh // 2, a - (kt - 1) + t_shift)
+            for a in range(kt) for i in range(kh) for j in range(kw)]
     n_total = pw.shape[0]
     ns = n_total if n_store is None else n_store
     ldc = (ns + 7) // 8 * 8
-    dims, strides = _view5(x)
+    dims, strides = _view5(xin)
     geom = _geom(T, H, W, n_total, _ntile(n_total), n_store=ns)
     if act_norm is not None and n_total <= 384:
-        out = torch.empty((T, H, W, ldc), dtype=torch.bfloat16, device=x.device) if want_raw else None
-        act = torch.empty((T, H, W, ldc), dtype=torch.bfloat16, device=x.device)
-        ops.conv_igemm(x, dims, strides, pw, taps, cin_p, geom, pb, out, residual=residual, clamp=clamp,
+        out = _alloc(T, H, W, ldc, x.device) if want_raw else None
+        act = _alloc(T, H, W, ldc, x.device)
+        ops.conv_igemm(xin, dims, strides, pw, taps, cin_p, geom, pb, out, residual=residual, clamp=clamp,
                        act_out=act, act_gamma=_vec(act_norm, "gamma", act_norm.gamma))
         return out, act
-    out = torch.empty((T, H, W, ldc), dtype=torch.bfloat16, device=x.device)
-    if ldc != ns:
-        out.zero_()
-    ops.conv_igemm(x, dims, strides, pw, taps, cin_p, geom, pb, out, residual=residual, clamp=clamp)
+    out = _alloc(T, H, W, ldc, x.device, zero=(ldc != ns))
+    ops.conv_igemm(xin, dims, strides, pw, taps, cin_p, geom, pb, out, residual=residual, clamp=clamp)
     if act_norm is not None:
         return out, rms_silu(out, act_norm)
     return out
@@ -293,14 +362,14 @@ def conv1x1(x, conv, out_ld=None):
     b = _bf(conv, "b1x1", conv.bias)
     cout = w.shape[0]
     ld = cout if out_ld is None else out_ld
-    out = torch.zeros((T, H, W, ld), dtype=torch.bfloat16, device=x.device) if ld != cout else \
-        torch.empty((T, H, W, ld), dtype=torch.bfloat16, device=x.device)
+    out = _alloc(T, H, W, ld, x.device, zero=(ld != cout))
     ops.gemm(x.reshape(-1, C)[:, :w.shape[1]], w, b, "bias", out=out.reshape(-1, ld)[:, :cout])
     return out
 
 
 def rms_silu(x, norm, silu=True):
-    return ops.rms_silu_cl(x, _vec(norm, "gamma", norm.gamma), silu=silu)
+    out = _alloc(*x.shape, x.device)
+    return ops.rms_silu_cl(x, _vec(norm, "gamma", norm.gamma), silu=silu, out=out)
 
 
 def res_block(x, blk, x_act=None, next_norm=None):
@@ -332,7 +401,9 @@ def attn_block(x, blk):
         vt[:, :n] = v.t()
         ops.gemm(p, vt[:, :n], None, "bias", out=o[t])
     a = conv1x1(o.reshape(T, H, W, C), blk.proj)
-    return x + a
+    out = _alloc(T, H, W, C, x.device)
+    torch.add(x, a, out=out)
+    return out
 
 
 def downsample(x, rs):
@@ -346,12 +417,12 @@ def downsample(x, rs):
     strides = (2 * x.stride(2), x.stride(1), 2 * x.stride(1), x.stride(0))
     taps = [((dw % 2) * C, dw // 2, dh % 2, dh // 2, 0) for dh in range(3) for dw in range(3)]
     n_total = pw.shape[0]
-    y = torch.empty((T, H2, W2, n_total), dtype=torch.bfloat16, device=x.device)
+    y = _alloc(T, H2, W2, n_total, x.device)
     ops.conv_igemm(x, dims, strides, pw, taps, cin_p, _geom(T, H2, W2, n_total, _ntile(n_total)), pb, y)
     if rs.mode == "downsample3d" and T > 1:
         tw, tb, tcin = pack_conv(rs.time_conv)
         To = (T - 1) // 2
-        z = torch.empty((1 + To, H2, W2, n_total), dtype=torch.bfloat16, device=x.device)
+        z = _alloc(1 + To, H2, W2, n_total, x.device)
         z[0].copy_(y[0])
         d5, s5 = _view5(y)
         ttaps = [(0, 0, 0, 0, a) for a in range(3)]
@@ -364,23 +435,46 @@ def downsample(x, rs):
 def upsample(x, rs):
     """reference :80-89, :107-145."""
     T, H, W, C = x.shape
-    if rs.mode == "upsample3d" and T > 1:
+    first = _SHARD is None or _SHARD.rank == 0        # does this rank hold global frame 0?
+    if rs.mode == "upsample3d" and (T > 1 or not first):
         tw, tb, tcin = pack_conv(rs.time_conv)                # [2C, 3*C]
-        To = 1 + 2 * (T - 1)
-        z = torch.empty((To, H, W, C), dtype=torch.bfloat16, device=x.device)
-        z[0].copy_(x[0])
-        xs = x[1:]
-        d5, s5 = _view5(xs)
-        ttaps = [(0, 0, 0, 0, a - 2) for a in range(3)]
         n_total = tw.shape[0]
-        # channels [0,C) -> frame 1+2t, channels [C,2C) -> frame 2+2t
-        ops.conv_igemm(xs, d5, s5, tw, ttaps, tcin, _geom(T - 1, H, W, n_total, _ntile(n_total), ot=(2, 1), half=C),
-                       tb, z)
+        if _SHARD is None:
+            To = 1 + 2 * (T - 1)
+            z = _alloc(To, H, W, C, x.device)
+            z[0].copy_(x[0])
+            xs = x[1:]
+            d5, s5 = _view5(xs)
+            ttaps = [(0, 0, 0, 0, a - 2) for a in range(3)]
+            # channels [0,C) -> frame 1+2t, channels [C,2C) -> frame 2+2t
+            ops.conv_igemm(xs, d5, s5, tw, ttaps, tcin,
+                           _geom(T - 1, H, W, n_total, _ntile(n_total), ot=(2, 1), half=C), tb, z)
+        else:
+            # The temporal conv runs over global frames 1.. with zero history (frame 0 is NOT part of it).  Rank 0
+            # therefore ships [0, frame1] when it owns only two frames; every other rank ships its last two.
+            xh = _haloed(x)
+            send = None
+            if first and T < 3:
+                send = torch.zeros_like(xh[-2:])
+                if T == 2:
+                    send[1].copy_(x[1])
+            _SHARD.exchange(xh, send=send)
+            skip = 1 if first else 0                              # frame 0 bypasses the conv (:107-112)
+            To = (1 if first else 0) + 2 * (T - skip)
+            z = _alloc(To, H, W, C, x.device)
+            if first:
+                z[0].copy_(x[0])
+                xh[1].zero_()                                     # history before global frame 1 is zero padding
+            d5, s5 = _view5(xh)
+            ttaps = [(0, 0, 0, 0, a + skip) for a in range(3)]    # own frame t (+skip) sits at xh[2 + skip + t]
+            if T - skip > 0:
+                ops.conv_igemm(xh, d5, s5, tw, ttaps, tcin,
+                               _geom(T - skip, H, W, n_total, _ntile(n_total), ot=(2, skip), half=C), tb, z)
         x = z
         T = To
     packs, cin_p = pack_upsample_conv(rs.resample[1])
     cout = rs.resample[1].weight.shape[0]
-    y = torch.empty((T, 2 * H, 2 * W, cout), dtype=torch.bfloat16, device=x.device)
+    y = _alloc(T, 2 * H, 2 * W, cout, x.device)
     d5, s5 = _view5(x)
     for (ph, pw_), (w4, b4, taps) in packs.items():
         n_total = w4.shape[0]
@@ -458,9 +552,13 @@ class AutoencoderKLWan_(nn.Module):
         logvar = ops.cl_to_nchw(h[..., z:], z)
         return torch.cat([mu, logvar], dim=0)[None]
 
-    def decode(self, z, scale):
+    def decode(self, z, scale, shard=None):
         """z [1, 16, f, h, w] (normalised) -> [1, 3, 4(f-1)+1, 8h, 8w] (:550-575); clamp is applied by the caller
-        in the reference (:669) and fused into the last convolution here."""
+        in the reference (:669) and fused into the last convolution here.
+
+        shard: optional TimeShard — the latent frames are split into contiguous per-rank ranges, every causal
+        convolution exchanges a 2-frame halo with the left neighbour, and the decoded frames are all-gathered."""
+        global _SHARD
         self._check(z)
         if z.shape[0] != 1:
             raise VcofError("decode expects batch 1 (the reference loops over the batch, :667-674)")
@@ -469,13 +567,34 @@ class AutoencoderKLWan_(nn.Module):
         inv_std = scale[1].to(z.device, torch.bfloat16).float().contiguous()
         h = ops.nchw_to_cl(z[0].to(torch.bfloat16).contiguous(), self.z_dim, div=inv_std, add=mean)
         h = conv1x1(h, self.conv2, out_ld=32)                  # 16 -> 16, stored in a 32-channel (zero padded) tensor
-        h = conv_causal(h, dec.conv1)
-        h, a = self._run(h, dec.middle)
-        h, a = self._run(h, dec.upsamples, a, tail_norm=dec.head[0])
-        if a is None:
-            a = rms_silu(h, dec.head[0])
-        h = conv_causal(a, dec.head[2], clamp=1.0, n_store=3)  # [T, H, W, 8] (3 real channels)
-        return ops.cl_to_nchw(h, 3)[None]
+        f = h.shape[0]
+        sharded = shard is not None and shard.world > 1 and f >= 2 * shard.world
+        if sharded:
+            base, extra = divmod(f, shard.world)
+            sizes = [base + (1 if r < extra else 0) for r in range(shard.world)]
+            a = sum(sizes[:shard.rank])
+            _SHARD = shard
+            own = _alloc(sizes[shard.rank], h.shape[1], h.shape[2], h.shape[3], h.device)
+            own.copy_(h[a:a + sizes[shard.rank]])
+            h = own
+        try:
+            h = conv_causal(h, dec.conv1)
+            h, a_ = self._run(h, dec.middle)
+            h, a_ = self._run(h, dec.upsamples, a_, tail_norm=dec.head[0])
+            if a_ is None:
+                a_ = rms_silu(h, dec.head[0])
+            h = conv_causal(a_, dec.head[2], clamp=1.0, n_store=3)  # [T, H, W, 8] (3 real channels)
+        finally:
+            _SHARD = None
+        out = ops.cl_to_nchw(h, 3)                                   # [3, T_r, H, W]
+        if sharded:
+            counts = [4 * n - (3 if r == 0 else 0) for r, n in enumerate(sizes)]
+            pad = torch.zeros((3, max(counts)) + tuple(out.shape[2:]), dtype=out.dtype, device=out.device)
+            pad[:, :out.shape[1]] = out
+            allp = torch.empty((shard.world,) + tuple(pad.shape), dtype=out.dtype, device=out.device)
+            shard.dist.all_gather_into_tensor(allp, pad, group=shard.group)
+            out = torch.cat([allp[r, :, :counts[r]] for r in range(shard.world)], dim=1)
+        return out[None]
 
     def clear_cache(self):
         """The reference's streaming caches do not exist here; kept for API compatibility (:589-596)."""
@@ -553,8 +672,16 @@ class AutoencoderKLWan(nn.Module):
         posterior = DiagonalGaussianDistribution(self._encode(x))
         return AutoencoderKLOutput(latent_dist=posterior) if return_dict else (posterior,)
 
+    def enable_temporal_sharding(self, group=None):
+        """Decode with the frames sharded over the ranks of `group` (default WORLD): 2-frame halo exchange per
+        causal convolution (TimeShard); single-rank behaviour is unchanged.  Clips with fewer than two latent
+        frames per rank (e.g. the 1-latent grounding segment) are decoded redundantly on every rank."""
+        self._shard = TimeShard(group)
+
     def _decode(self, zs):
-        return DecoderOutput(sample=torch.cat([self.model.decode(u.unsqueeze(0), self.scale) for u in zs], dim=0))
+        shard = getattr(self, "_shard", None)
+        return DecoderOutput(sample=torch.cat([self.model.decode(u.unsqueeze(0), self.scale, shard=shard)
+                                               for u in zs], dim=0))
 
     def decode(self, z, return_dict=True):
         decoded = self._decode(z).sample
