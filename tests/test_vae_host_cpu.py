@@ -49,3 +49,46 @@ def test_state_dict_keys_match_reference_vae():
     ref = {k: tuple(v.shape) for k, v in make_vae_params(VAEConfig(), seed=0).items()}
     assert ours == ref      # make_vae_params loads strict=True into the reference class (tools/gen_golden.py)
     assert len(ours) == 194
+
+
+class _FakeShard:
+    """Sequential stand-in for videocof_b200.vae.TimeShard: halo data only flows from rank r to r+1, so the ranks
+    can be executed one after the other in one process with a mailbox."""
+    HALO = 2
+
+    def __init__(self, rank, world, mailbox, outs):
+        self.rank, self.world, self.mailbox, self.outs = rank, world, mailbox, outs
+
+    def exchange(self, xh, send=None):
+        if self.rank > 0:
+            xh[:2].copy_(self.mailbox[self.rank - 1].pop(0))
+        else:
+            xh[:2].zero_()
+        if self.rank + 1 < self.world:
+            self.mailbox[self.rank].append((xh[-2:] if send is None else send).clone())
+
+    def gather_frames(self, out, counts):
+        assert out.shape[1] == counts[self.rank]
+        self.outs[self.rank] = out
+        return out
+
+
+@pytest.mark.parametrize("world,frames", [(2, 5), (3, 7), (2, 4)])
+def test_vae_temporal_sharding_matches_unsharded(world, frames, model, monkeypatch):
+    """Frame-range sharding with 2-frame halos (TimeShard) reproduces the un-sharded decode."""
+    vcof_emulator.install(monkeypatch)
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(1, 16, frames, 2, 3, generator=g).bfloat16()
+    with torch.no_grad():
+        ref = model.decode(z).sample[0]
+        mailbox = [[] for _ in range(world)]
+        outs = [None] * world
+        for r in range(world):
+            model.model.decode(z, model.scale, shard=_FakeShard(r, world, mailbox, outs))
+    got = torch.cat(outs, dim=1)
+    assert got.shape == ref.shape
+    # the CPU emulator's fp32 matmuls are not bit-reproducible across batch shapes (bf16 rounding flips a few
+    # values); on the GPU the per-position math is identical and tools/vae_shard_check.py demands exact equality
+    rel = float((got.float() - ref.float()).norm() / ref.float().norm())
+    assert rel < 1e-2, rel
+    assert all(len(m) == 0 for m in mailbox[:-1])

@@ -90,6 +90,9 @@ def rms_silu_cl(x, gamma, silu=True, out=None):
     y = (y * gamma).to(torch.bfloat16).float()
     if silu:
         y = torch.nn.functional.silu(y)
+    if out is not None:
+        out.copy_(y.to(torch.bfloat16))
+        return out
     return y.to(torch.bfloat16)
 
 

@@ -275,6 +275,15 @@ class TimeShard:
             xh[:self.HALO].copy_(recv)
 
 
+    def gather_frames(self, out, counts):
+        """All-gather per-rank frame ranges [C, counts[r], H, W] into the full clip on every rank."""
+        pad = torch.zeros((out.shape[0], max(counts)) + tuple(out.shape[2:]), dtype=out.dtype, device=out.device)
+        pad[:, :out.shape[1]] = out
+        allp = torch.empty((self.world,) + tuple(pad.shape), dtype=out.dtype, device=out.device)
+        self.dist.all_gather_into_tensor(allp, pad, group=self.group)
+        return torch.cat([allp[r, :, :counts[r]] for r in range(self.world)], dim=1)
+
+
 _SHARD = None      # active TimeShard of the current encode/decode call (None = single GPU)
 
 
@@ -464,7 +473,7 @@ def upsample(x, rs):
             z = _alloc(To, H, W, C, x.device)
             if first:
                 z[0].copy_(x[0])
-                xh[1].zero_()                                     # history before global frame 1 is zero padding
+                xh[2].zero_()     # global frame 0 is not part of the time_conv sequence: it reads as zero padding
             d5, s5 = _view5(xh)
             ttaps = [(0, 0, 0, 0, a + skip) for a in range(3)]    # own frame t (+skip) sits at xh[2 + skip + t]
             if T - skip > 0:
@@ -589,11 +598,7 @@ class AutoencoderKLWan_(nn.Module):
         out = ops.cl_to_nchw(h, 3)                                   # [3, T_r, H, W]
         if sharded:
             counts = [4 * n - (3 if r == 0 else 0) for r, n in enumerate(sizes)]
-            pad = torch.zeros((3, max(counts)) + tuple(out.shape[2:]), dtype=out.dtype, device=out.device)
-            pad[:, :out.shape[1]] = out
-            allp = torch.empty((shard.world,) + tuple(pad.shape), dtype=out.dtype, device=out.device)
-            shard.dist.all_gather_into_tensor(allp, pad, group=shard.group)
-            out = torch.cat([allp[r, :, :counts[r]] for r in range(shard.world)], dim=1)
+            out = shard.gather_frames(out, counts)
         return out[None]
 
     def clear_cache(self):
