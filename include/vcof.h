@@ -132,6 +132,13 @@ int vcof_softmax_rows(const float* s, long long lds, void* p, long long ldp, int
  * Pins the descriptor conventions the GEMM / attention kernels depend on. */
 int vcof_debug_umma_probe(const void* a, const void* b, float* d, int mode, void* stream);
 
+/* Sustained TMA box-load rate: every CTA streams `iters` boxes of the given rank-2 / rank-5 bf16 view through an
+ * 8-deep shared-memory ring (no compute); cycles[cta] receives the elapsed SM clocks.  Explains the feed-rate
+ * ceilings quoted in profiles/ (rows of 64 B vs 128 B, strided pixel slices vs contiguous rows). */
+int vcof_debug_tma_probe(const void* base, int rank, const long long* dims, const long long* strides, const int* box,
+                         int swizzle_bytes, int iters, const int* coords, int step_dim, int step, int wrap,
+                         unsigned long long* cycles, int grid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,85 @@
+// tma_probe.cu — diagnostic: sustained TMA tile-load throughput per SM for the box shapes libvcof uses.
+// One producer lane issues box loads into a shared-memory ring, one consumer lane waits for them and frees
+// the slots; nothing else runs.  Reports achieved bytes/clk/SM so a kernel's feed rate can be compared
+// with what the TMA unit can deliver for that box geometry (rows of 64 B vs 128 B, 2-D vs 5-D views).
+// Used by tools/tma_probe.py; results in profiles/.
+#include "vcof_common.cuh"
+#include "../../include/vcof.h"
+
+namespace vcof {
+
+struct TmaProbeArgs {
+  int rank;             // tensor-map rank (2 or 5)
+  int box_bytes;        // bytes per box
+  int iters;            // boxes per CTA
+  int c[5];             // base coordinates
+  int step_dim, step;   // coordinate advanced per iteration (wraps at `wrap`)
+  int wrap;
+  unsigned long long* cycles;  // [gridDim.x]
+};
+
+__global__ void __launch_bounds__(64, 1)
+tma_probe_kernel(const __grid_constant__ CUtensorMap tm, TmaProbeArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int S = 8;
+  __shared__ __align__(8) uint64_t full[S], empty[S];
+  const int stage_bytes = (p.box_bytes + 1023) / 1024 * 1024;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const unsigned long long t0 = clock64();
+  if (threadIdx.x == 0) {
+    int s = 0; uint32_t ph = 0;
+    for (int i = 0; i < p.iters; ++i) {
+      mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+      mbar_expect_tx(smem_u32(&full[s]), p.box_bytes);
+      int c[5] = {p.c[0], p.c[1], p.c[2], p.c[3], p.c[4]};
+      c[p.step_dim] += ((i * p.step) + blockIdx.x * 7) % p.wrap;
+      if (p.rank == 2) tma_load_2d(smem_u32(smem + s * stage_bytes), &tm, smem_u32(&full[s]), c[0], c[1]);
+      else tma_load_5d(smem_u32(smem + s * stage_bytes), &tm, smem_u32(&full[s]), c[0], c[1], c[2], c[3], c[4]);
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+  } else if (threadIdx.x == 32) {
+    int s = 0; uint32_t ph = 0;
+    for (int i = 0; i < p.iters; ++i) {
+      mbar_wait(smem_u32(&full[s]), ph);
+      mbar_arrive(smem_u32(&empty[s]));
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) p.cycles[blockIdx.x] = clock64() - t0;
+}
+
+}  // namespace vcof
+
+using namespace vcof;
+
+extern "C" int vcof_debug_tma_probe(const void* base, int rank, const long long* dims, const long long* strides,
+                                    const int* box, int swizzle_bytes, int iters, const int* coords, int step_dim,
+                                    int step, int wrap, unsigned long long* cycles, int grid, void* stream) {
+  CUtensorMap tm;
+  uint64_t d[5], s[4];
+  uint32_t b[5];
+  long long box_elems = 1;
+  for (int i = 0; i < rank; ++i) { d[i] = (uint64_t)dims[i]; b[i] = (uint32_t)box[i]; box_elems *= box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = (uint64_t)strides[i] * 2;
+  int rc = make_tmap_nd_bf16(&tm, base, rank, d, s, b, swizzle_bytes);
+  if (rc) return rc;
+  TmaProbeArgs a;
+  a.rank = rank;
+  a.box_bytes = (int)(box_elems * 2);
+  a.iters = iters;
+  for (int i = 0; i < 5; ++i) a.c[i] = i < rank ? coords[i] : 0;
+  a.step_dim = step_dim; a.step = step; a.wrap = wrap;
+  a.cycles = cycles;
+  const int smem = 8 * ((a.box_bytes + 1023) / 1024 * 1024) + 1024;
+  VCOF_REQUIRE(smem <= 200 * 1024, "vcof_debug_tma_probe: box too large");
+  VCOF_CHECK_CUDA(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tma_probe_kernel<<<grid, 64, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm, a);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
