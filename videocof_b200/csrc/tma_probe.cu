@@ -15,6 +15,7 @@ struct TmaProbeArgs {
   int c[5];             // base coordinates
   int step_dim, step;   // coordinate advanced per iteration (wraps at `wrap`)
   int wrap;
+  int stages;           // ring depth: ~192 KB in flight regardless of the box size
   unsigned long long* cycles;  // [gridDim.x]
 };
 
@@ -22,8 +23,8 @@ __global__ void __launch_bounds__(64, 1)
 tma_probe_kernel(const __grid_constant__ CUtensorMap tm, TmaProbeArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int S = 8;
-  __shared__ __align__(8) uint64_t full[S], empty[S];
+  __shared__ __align__(8) uint64_t full[24], empty[24];
+  const int S = p.stages;
   const int stage_bytes = (p.box_bytes + 1023) / 1024 * 1024;
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
@@ -76,8 +77,11 @@ extern "C" int vcof_debug_tma_probe(const void* base, int rank, const long long*
   for (int i = 0; i < 5; ++i) a.c[i] = i < rank ? coords[i] : 0;
   a.step_dim = step_dim; a.step = step; a.wrap = wrap;
   a.cycles = cycles;
-  const int smem = 8 * ((a.box_bytes + 1023) / 1024 * 1024) + 1024;
-  VCOF_REQUIRE(smem <= 200 * 1024, "vcof_debug_tma_probe: box too large");
+  const int stage_bytes = (a.box_bytes + 1023) / 1024 * 1024;
+  a.stages = (192 * 1024) / stage_bytes;
+  if (a.stages > 24) a.stages = 24;
+  VCOF_REQUIRE(a.stages >= 2, "vcof_debug_tma_probe: box too large");
+  const int smem = a.stages * stage_bytes + 1024;
   VCOF_CHECK_CUDA(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   tma_probe_kernel<<<grid, 64, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm, a);
   VCOF_CHECK_CUDA(cudaGetLastError());
