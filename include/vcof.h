@@ -91,8 +91,11 @@ int vcof_linear_f32(const float* x, const void* w, const void* bias, float* out,
  * patch feeds the MMA directly; TMA zero-fill provides the spatial and causal-temporal padding.
  *   x_dims[5]    (c_inner, W, P, H, T) of the input view (P = 1, or 2 for the stride-2 "parity" view
  *                of the down-sampler where c_inner = 2*Cin); x_strides[4]: element strides of dims 1..4
- *   w            bf16 [n_total, k_total], k = tap * cin + c  (n_total padded to a multiple of 16)
- *   taps[5*i..]  (c_base, dw, p, dh, dt): coordinate offsets of tap i added to the tile origin
+ *   taps[5*i..]  (c_base, dw, p, dh, dt): coordinate offsets of tap i added to the tile origin; taps come in groups
+ *                of `tgroup` (1 or 3) consecutive entries that differ only by dt, dt+1, dt+2 — one TMA box with a
+ *                t-extent of tgroup feeds the whole group (the TMA unit's cost is per box)
+ *   w            bf16 [k_total/32, n_total, 32]: slice ((group * cin/32 + chunk) * tgroup + j) holds the 32 input
+ *                channels `chunk` of tap (group, j) for every output channel (n_total padded to a multiple of 16)
  *   geom[16]     T_out, H_out, W_out, t_stride, n_total, n_tile, ot_mul, ot_add, oh_mul, oh_add, ow_mul,
  *                ow_add, Hs, Ws, interleave_half, n_store — output position (t,h,w) is stored at
  *                [t*ot_mul+ot_add, h*oh_mul+oh_add, w*ow_mul+ow_add] of a [*, Hs, Ws, ldc] tensor;
@@ -102,7 +105,7 @@ int vcof_linear_f32(const float* x, const void* w, const void* bias, float* out,
  *                opens the NEXT layer (wan_vae.py:197-201) — with the same addressing; `out` may then be NULL.
  * Replaces CausalConv3d / Conv2d of wan_vae.py:21-40, 80-100, 107-163, 190-224, 318-320, 423-425. */
 int vcof_conv_igemm(const void* x, const long long* x_dims, const long long* x_strides, const void* w,
-                    int k_total, const short* taps, int ntaps, int cin, const int* geom, const float* bias,
+                    int k_total, const short* taps, int ntaps, int tgroup, int cin, const int* geom, const float* bias,
                     const void* residual, void* out, long long ldc, float clamp, void* act_out,
                     const float* act_gamma, void* stream);
 

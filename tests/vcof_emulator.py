@@ -23,7 +23,7 @@ def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
 
 
 def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=None, clamp=0.0, act_out=None,
-               act_gamma=None):
+               act_gamma=None, tgroup=1):
     (T, H, W, t_stride, n_total, n_tile, ot_mul, ot_add, oh_mul, oh_add, ow_mul, ow_add, Hs, Ws, half, n_store) = geom
     C_in, Wd, Pd, Hd, Td = x_dims
     sW, sP, sH, sT = x_strides
@@ -32,7 +32,12 @@ def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=Non
     store = x.untyped_storage()
     full = torch.empty(0, dtype=x.dtype).set_(store)          # whole storage as a flat tensor
     acc = torch.zeros(T, H, W, n_total)
-    wf = w.float()
+    ccn = cin // 32
+    assert len(taps) % tgroup == 0
+    for g0 in range(0, len(taps), tgroup):            # contract: group members differ only by consecutive dt
+        for j in range(1, tgroup):
+            assert taps[g0 + j][:4] == taps[g0][:4] and taps[g0 + j][4] == taps[g0][4] + j
+    w5 = w.float().view(len(taps) // tgroup, ccn, tgroup, n_total, 32)   # [G, cc, tg, n, 32]
     tt, hh, ww = torch.meshgrid(torch.arange(T), torch.arange(H), torch.arange(W), indexing="ij")
     cc = torch.arange(cin)
     for i, (c_base, dw, p, dh, dt) in enumerate(taps):
@@ -45,7 +50,8 @@ def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=Non
         ch_ok = ch < C_in
         gather = full[(idx[..., None] + ch.clamp(max=C_in - 1)[None, None, None, :])].float()
         gather = gather * ok[..., None] * ch_ok[None, None, None, :]
-        acc += gather @ wf[:, i * cin:(i + 1) * cin].t()
+        w_tap = w5[i // tgroup, :, i % tgroup].permute(1, 0, 2).reshape(n_total, cin)   # [n, cin]
+        acc += gather @ w_tap.t()
     if bias is not None:
         acc = acc + bias
     if act_out is not None:

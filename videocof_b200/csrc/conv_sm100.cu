@@ -54,8 +54,9 @@ struct ConvArgs {
   int interleave_half;        // > 0: channels >= this go to frame+1 and are stored at (n - half)
   int n_store;                // channels actually stored per position (<= n_total)
   int stages, stage_bytes;    // TMA ring geometry chosen at launch
-  int group;                  // 32-channel slices per ring stage (1..3): one mbarrier round-trip then covers
-                              // >= ~300 MMA cycles even for N = 96, so the single MMA-issuing thread keeps up
+  int tgroup;                 // consecutive taps that differ only in dt (3 for k_t = 3, else 1): ONE 5-D box with
+                              // t-extent tgroup and ONE rank-3 weight box feed tgroup taps — the TMA unit's cost
+                              // is per box (profiles/r1_tma_probe.txt), so boxes must be as large as possible
   const float* bias;          // [n_total] fp32 or nullptr
   const bf16* residual;       // same addressing as out, or nullptr
   bf16* out;                  // raw output, may be nullptr when only act_out is wanted
@@ -108,7 +109,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int tiles_w = (p.W_out + 15) / 16, tiles_h = (p.H_out + 7) / 8;
   const int n_tiles = (p.n_total + p.n_tile - 1) / p.n_tile;
   const int num_tiles = p.T_out * tiles_h * tiles_w * n_tiles;
-  const int num_k = p.ntaps * (p.cin_chunks / p.group);
+  const int ngroups = p.ntaps / p.tgroup;
+  const int num_k = ngroups * p.cin_chunks;
   const int nacc = (p.n_tile <= 256) ? 2 : 1;            // accumulator buffers in TMEM
   const int nsub = (p.n_tile <= 256) ? 1 : 2;            // MMAs per k-step (N <= 256 each)
   const int n_sub = p.n_tile / nsub;
@@ -131,21 +133,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int t, h0, w0, n0;
         decode(tile, t, h0, w0, n0);
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const ConvTap tp = p.taps[tap];
-          for (int cc = 0; cc < p.cin_chunks; cc += p.group) {
+        for (int g = 0; g < ngroups; ++g) {
+          const ConvTap tp = p.taps[g * p.tgroup];            // first tap of the group (lowest dt)
+          for (int cc = 0; cc < p.cin_chunks; ++cc) {
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            mbar_expect_tx(bar_full + 8 * s, p.group * (kCvABytes + b_bytes));
+            mbar_expect_tx(bar_full + 8 * s, p.tgroup * (kCvABytes + b_bytes));
             uint8_t* st = smem + s * kCvStage;
-            for (int g = 0; g < p.group; ++g) {
-              uint8_t* sg = st + g * (kCvABytes + b_bytes);
-              tma_load_5d(smem_u32(sg), &tmX, bar_full + 8 * s, tp.c_base + (cc + g) * 32, w0 + tp.dw, tp.p,
-                          h0 + tp.dh, t * p.t_stride + tp.dt);
-              const int kk = tap * p.cin + (cc + g) * 32;
-              for (int j = 0; j < nsub; ++j)
-                tma_load_2d(smem_u32(sg + kCvABytes + j * n_sub * 64), &tmW, bar_full + 8 * s, kk,
-                            n0 + j * n_sub);
-            }
+            // [32 c, 16 w, 1, 8 h, tgroup t] -> tgroup consecutive 128x64B K-major tiles
+            tma_load_5d(smem_u32(st), &tmX, bar_full + 8 * s, tp.c_base + cc * 32, w0 + tp.dw, tp.p, h0 + tp.dh,
+                        t * p.t_stride + tp.dt);
+            const int slice = (g * p.cin_chunks + cc) * p.tgroup;
+            for (int j = 0; j < nsub; ++j)
+              tma_load_3d(smem_u32(st + p.tgroup * kCvABytes + j * p.tgroup * n_sub * 64), &tmW, bar_full + 8 * s, 0,
+                          n0 + j * n_sub, slice);
             if (++s == kCvStages) { s = 0; ph ^= 1; }
           }
         }
@@ -166,14 +166,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int k = 0; k < num_k; ++k) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          for (int g = 0; g < p.group; ++g) {
-            const uint32_t a_base = smem_u32(smem + s * kCvStage) + g * (kCvABytes + b_bytes);
-            const uint32_t b_base = a_base + kCvABytes;
+          const uint32_t a_stage = smem_u32(smem + s * kCvStage);
+          const uint32_t b_stage = a_stage + p.tgroup * kCvABytes;
+          for (int dt = 0; dt < p.tgroup; ++dt) {
+            const uint32_t a_base = a_stage + dt * kCvABytes;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               for (int j = 0; j < nsub; ++j)
                 umma_ss(d_tmem + j * n_sub, make_desc_kmajor_sw64(a_base + ks * 32),
-                        make_desc_kmajor_sw64(b_base + j * n_sub * 64 + ks * 32), idesc, (k | g | ks) != 0);
+                        make_desc_kmajor_sw64(b_stage + (j * p.tgroup + dt) * n_sub * 64 + ks * 32), idesc,
+                        (k | dt | ks) != 0);
             }
           }
           umma_commit(bar_empty + 8 * s);
@@ -422,7 +424,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, bf16* __restric
 using namespace vcof;
 
 extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const long long* x_strides,
-                               const void* w, int k_total, const short* taps, int ntaps, int cin,
+                               const void* w, int k_total, const short* taps, int ntaps, int tgroup, int cin,
                                const int* geom, const float* bias, const void* residual, void* out,
                                long long ldc, float clamp, void* act_out, const float* act_gamma,
                                void* stream) {
@@ -461,10 +463,17 @@ extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const lon
                "vcof_conv_igemm: n_total %d / n_tile %d must be multiples of 16, n_tile <= 384", a.n_total,
                a.n_tile);
   VCOF_REQUIRE(a.n_tile <= 256 || (a.n_tile / 2) % 16 == 0, "vcof_conv_igemm: n_tile/2 must be a multiple of 16");
-  a.group = a.n_tile <= 128 ? 3 : (a.n_tile <= 256 ? 2 : 1);
-  while (a.cin_chunks % a.group) --a.group;
-  a.stage_bytes = a.group * (kCvABytes + a.n_tile * 64);     // multiples of 512 B keep SW64 tiles aligned
+  VCOF_REQUIRE(tgroup >= 1 && tgroup <= 3 && ntaps % tgroup == 0, "vcof_conv_igemm: bad tap group %d", tgroup);
+  for (int g = 0; g < ntaps / tgroup; ++g)
+    for (int j = 1; j < tgroup; ++j) {
+      const ConvTap &u = a.taps[g * tgroup], &v = a.taps[g * tgroup + j];
+      VCOF_REQUIRE(v.c_base == u.c_base && v.dw == u.dw && v.p == u.p && v.dh == u.dh && v.dt == u.dt + j,
+                   "vcof_conv_igemm: taps of group %d must differ only by consecutive dt", g);
+    }
+  a.tgroup = tgroup;
+  a.stage_bytes = tgroup * (kCvABytes + a.n_tile * 64);      // multiples of 1 KB keep the SW64 tiles aligned
   a.stages = kCvData / a.stage_bytes;
+  VCOF_REQUIRE(a.stages >= 2, "vcof_conv_igemm: stage of %d bytes leaves no ring", a.stage_bytes);
   if (a.stages > kCvMaxStages) a.stages = kCvMaxStages;
   VCOF_REQUIRE(k_total == ntaps * cin, "vcof_conv_igemm: weight K %d != ntaps*cin %d", k_total, ntaps * cin);
   VCOF_REQUIRE(ldc % 8 == 0, "vcof_conv_igemm: ldc must be a multiple of 8");
@@ -472,14 +481,15 @@ extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const lon
   uint64_t dims[5], strides[4];
   for (int i = 0; i < 5; ++i) dims[i] = (uint64_t)x_dims[i];
   for (int i = 0; i < 4; ++i) strides[i] = (uint64_t)x_strides[i] * 2;
-  const uint32_t box[5] = {32, 16, 1, 8, 1};
+  const uint32_t box[5] = {32, 16, 1, 8, (uint32_t)tgroup};
   int rc = make_tmap_nd_bf16(&tmX, x, 5, dims, strides, box, 64);
   if (rc) return rc;
   const int nsub = a.n_tile <= 256 ? 1 : 2;
-  uint64_t wd[2] = {(uint64_t)k_total, (uint64_t)a.n_total};
-  uint64_t ws[1] = {(uint64_t)k_total * 2};
-  uint32_t wb[2] = {32, (uint32_t)(a.n_tile / nsub)};
-  rc = make_tmap_nd_bf16(&tmW, w, 2, wd, ws, wb, 64);
+  // weights: [slices, n_total, 32] with slice = ((tap_group * cin_chunks + chunk) * tgroup + j)
+  uint64_t wd[3] = {32, (uint64_t)a.n_total, (uint64_t)(k_total / 32)};
+  uint64_t ws[2] = {64, (uint64_t)a.n_total * 64};
+  uint32_t wb[3] = {32, (uint32_t)(a.n_tile / nsub), (uint32_t)tgroup};
+  rc = make_tmap_nd_bf16(&tmW, w, 3, wd, ws, wb, 64);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {

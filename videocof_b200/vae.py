@@ -172,27 +172,32 @@ def _ver(*tensors):
     return tuple((t.data_ptr(), t._version, str(t.device), t.dtype) for t in tensors if t is not None)
 
 
-def _pack_taps(w_taps, bias, cin_p):
-    """w_taps: fp32 [Cout, Cin, ntaps] -> bf16 [Cout_p16, ntaps*cin_p] (k = tap*cin_p + c), bias fp32 [Cout_p16]."""
+def _pack_taps(w_taps, bias, cin_p, tgroup=1):
+    """w_taps: fp32 [Cout, Cin, ntaps] (taps ordered group-major, the `tgroup` dt-taps of a group adjacent) ->
+    bf16 [slices, Cout_p16, 32] with slice = ((group * cin_p/32 + chunk) * tgroup + j); bias fp32 [Cout_p16]."""
     cout, cin, ntaps = w_taps.shape
     cout_p = _pad16(cout)
     w = torch.zeros((cout_p, ntaps, cin_p), dtype=torch.float32, device=w_taps.device)
     w[:cout, :, :cin] = w_taps.permute(0, 2, 1)
+    w = w.view(cout_p, ntaps // tgroup, tgroup, cin_p // 32, 32).permute(1, 3, 2, 0, 4)   # [G, cc, tg, n, 32]
     b = torch.zeros(cout_p, dtype=torch.float32, device=w_taps.device)
     if bias is not None:
         b[:cout] = bias.float()
-    return w.reshape(cout_p, ntaps * cin_p).to(torch.bfloat16).contiguous(), b
+    return w.reshape(-1, cout_p, 32).to(torch.bfloat16).contiguous(), b
 
 
 def pack_conv(conv):
-    """nn.Conv3d [Cout,Cin,kt,kh,kw] / nn.Conv2d [Cout,Cin,kh,kw] -> (packed weight, bias, cin_p); taps ordered
-    (kt, kh, kw)-major."""
+    """nn.Conv3d [Cout,Cin,kt,kh,kw] / nn.Conv2d [Cout,Cin,kh,kw] -> (packed weight, bias, cin_p, tgroup); taps are
+    ordered (kh, kw)-major with the k_t temporal taps adjacent, so that one TMA box feeds all k_t of them."""
     def build():
         w = conv.weight.detach().float()
-        w = w.reshape(w.shape[0], w.shape[1], -1)
+        if w.dim() == 4:
+            w = w.unsqueeze(2)
+        kt = w.shape[2]
+        w = w.permute(0, 1, 3, 4, 2).reshape(w.shape[0], w.shape[1], -1)    # taps (i, j, a), a fastest
         cin_p = _pad32(w.shape[1])
-        pw, pb = _pack_taps(w, conv.bias.detach() if conv.bias is not None else None, cin_p)
-        return pw, pb, cin_p
+        pw, pb = _pack_taps(w, conv.bias.detach() if conv.bias is not None else None, cin_p, tgroup=kt)
+        return pw, pb, cin_p, kt
     return _cached(conv, "plain", _ver(conv.weight, conv.bias), build)
 
 
@@ -329,7 +334,7 @@ def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None, act_norm=None, 
 
     act_norm: an RMS_norm module whose norm+SiLU (the opening of the NEXT layer) is fused into the epilogue;
     returns (raw, act) then (raw is None when want_raw is False)."""
-    pw, pb, cin_p = pack_conv(conv)
+    pw, pb, cin_p, tg = pack_conv(conv)
     T, H, W, C = x.shape
     if C != cin_p:
         raise VcofError(f"conv input has {C} channels, packed weight expects {cin_p}")
@@ -344,8 +349,8 @@ def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None, act_norm=None, 
         _SHARD.exchange(xin)
         t_shift = TimeShard.HALO
     taps = [(0, j - kw // 2, 0, i - kh // 2, a - (kt - 1) + t_shift)
-            for a in range(kt) for i in range(kh) for j in range(kw)]
-    n_total = pw.shape[0]
+            for i in range(kh) for j in range(kw) for a in range(kt)]
+    n_total = pw.shape[1]
     ns = n_total if n_store is None else n_store
     ldc = (ns + 7) // 8 * 8
     dims, strides = _view5(xin)
@@ -354,10 +359,10 @@ def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None, act_norm=None, 
         out = _alloc(T, H, W, ldc, x.device) if want_raw else None
         act = _alloc(T, H, W, ldc, x.device)
         ops.conv_igemm(xin, dims, strides, pw, taps, cin_p, geom, pb, out, residual=residual, clamp=clamp,
-                       act_out=act, act_gamma=_vec(act_norm, "gamma", act_norm.gamma))
+                       act_out=act, act_gamma=_vec(act_norm, "gamma", act_norm.gamma), tgroup=tg)
         return out, act
     out = _alloc(T, H, W, ldc, x.device, zero=(ldc != ns))
-    ops.conv_igemm(xin, dims, strides, pw, taps, cin_p, geom, pb, out, residual=residual, clamp=clamp)
+    ops.conv_igemm(xin, dims, strides, pw, taps, cin_p, geom, pb, out, residual=residual, clamp=clamp, tgroup=tg)
     if act_norm is not None:
         return out, rms_silu(out, act_norm)
     return out
@@ -418,25 +423,25 @@ def attn_block(x, blk):
 def downsample(x, rs):
     """reference :91-100, :147-163."""
     conv = rs.resample[1]
-    pw, pb, cin_p = pack_conv(conv)
+    pw, pb, cin_p, _ = pack_conv(conv)
     T, H, W, C = x.shape
     H2, W2 = H // 2, W // 2
     # parity view (c_inner = pw*C + c, w2, ph, h2, t): input row 2*h2 + ph, column 2*w2 + pw
     dims = (2 * C, W2, 2, H2, T)
     strides = (2 * x.stride(2), x.stride(1), 2 * x.stride(1), x.stride(0))
     taps = [((dw % 2) * C, dw // 2, dh % 2, dh // 2, 0) for dh in range(3) for dw in range(3)]
-    n_total = pw.shape[0]
+    n_total = pw.shape[1]
     y = _alloc(T, H2, W2, n_total, x.device)
     ops.conv_igemm(x, dims, strides, pw, taps, cin_p, _geom(T, H2, W2, n_total, _ntile(n_total)), pb, y)
     if rs.mode == "downsample3d" and T > 1:
-        tw, tb, tcin = pack_conv(rs.time_conv)
+        tw, tb, tcin, ttg = pack_conv(rs.time_conv)
         To = (T - 1) // 2
         z = _alloc(1 + To, H2, W2, n_total, x.device)
         z[0].copy_(y[0])
         d5, s5 = _view5(y)
         ttaps = [(0, 0, 0, 0, a) for a in range(3)]
         ops.conv_igemm(y, d5, s5, tw, ttaps, tcin, _geom(To, H2, W2, n_total, _ntile(n_total), ot=(1, 1), t_stride=2),
-                       tb, z)
+                       tb, z, tgroup=ttg)
         y = z
     return y
 
@@ -446,8 +451,8 @@ def upsample(x, rs):
     T, H, W, C = x.shape
     first = _SHARD is None or _SHARD.rank == 0        # does this rank hold global frame 0?
     if rs.mode == "upsample3d" and (T > 1 or not first):
-        tw, tb, tcin = pack_conv(rs.time_conv)                # [2C, 3*C]
-        n_total = tw.shape[0]
+        tw, tb, tcin, ttg = pack_conv(rs.time_conv)           # 2C outputs, 3 temporal taps
+        n_total = tw.shape[1]
         if _SHARD is None:
             To = 1 + 2 * (T - 1)
             z = _alloc(To, H, W, C, x.device)
@@ -457,7 +462,7 @@ def upsample(x, rs):
             ttaps = [(0, 0, 0, 0, a - 2) for a in range(3)]
             # channels [0,C) -> frame 1+2t, channels [C,2C) -> frame 2+2t
             ops.conv_igemm(xs, d5, s5, tw, ttaps, tcin,
-                           _geom(T - 1, H, W, n_total, _ntile(n_total), ot=(2, 1), half=C), tb, z)
+                           _geom(T - 1, H, W, n_total, _ntile(n_total), ot=(2, 1), half=C), tb, z, tgroup=ttg)
         else:
             # The temporal conv runs over global frames 1.. with zero history (frame 0 is NOT part of it).  Rank 0
             # therefore ships [0, frame1] when it owns only two frames; every other rank ships its last two.
@@ -478,7 +483,8 @@ def upsample(x, rs):
             ttaps = [(0, 0, 0, 0, a + skip) for a in range(3)]    # own frame t (+skip) sits at xh[2 + skip + t]
             if T - skip > 0:
                 ops.conv_igemm(xh, d5, s5, tw, ttaps, tcin,
-                               _geom(T - skip, H, W, n_total, _ntile(n_total), ot=(2, skip), half=C), tb, z)
+                               _geom(T - skip, H, W, n_total, _ntile(n_total), ot=(2, skip), half=C), tb, z,
+                               tgroup=ttg)
         x = z
         T = To
     packs, cin_p = pack_upsample_conv(rs.resample[1])
@@ -486,7 +492,7 @@ def upsample(x, rs):
     y = _alloc(T, 2 * H, 2 * W, cout, x.device)
     d5, s5 = _view5(x)
     for (ph, pw_), (w4, b4, taps) in packs.items():
-        n_total = w4.shape[0]
+        n_total = w4.shape[1]
         ops.conv_igemm(x, d5, s5, w4, taps, cin_p,
                        _geom(T, H, W, n_total, _ntile(n_total), oh=(2, ph), ow=(2, pw_), Hs=2 * H, Ws=2 * W,
                              n_store=cout), b4, y)
