@@ -110,7 +110,8 @@ int vcof_conv_igemm(const void* x, const long long* x_dims, const long long* x_s
                     const float* act_gamma, void* stream);
 
 /* y = [silu]( x / max(||x||_2, 1e-12) * sqrt(C) * gamma ) per position, channels-last; RMS_norm (+ nn.SiLU)
- * of wan_vae.py:43-58 with the bf16 rounding points of the reference's ATen op chain. */
+ * of wan_vae.py:43-58, fp32 intermediates and one bf16 rounding at the store (the reference's ATen chain rounds
+ * after every op). */
 int vcof_rms_silu_cl(const void* x, long long ldx, const float* gamma, void* y, long long ldy,
                      long long npos, int C, int silu, void* stream);
 

@@ -89,11 +89,10 @@ def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=Non
 
 
 def rms_silu_cl(x, gamma, silu=True, out=None):
+    """y = [silu](x / max(||x||, 1e-12) * sqrt(C) * gamma): fp32 intermediates, one rounding at the store."""
     xf = x.float()
-    dn = xf.pow(2).sum(-1, keepdim=True).sqrt().to(torch.bfloat16).float().clamp_min(1e-12)
-    y = (xf / dn).to(torch.bfloat16).float()
-    y = (y * (x.shape[-1] ** 0.5)).to(torch.bfloat16).float()
-    y = (y * gamma).to(torch.bfloat16).float()
+    inv = (x.shape[-1] ** 0.5) / xf.pow(2).sum(-1, keepdim=True).sqrt().clamp_min(1e-12)
+    y = xf * inv * gamma
     if silu:
         y = torch.nn.functional.silu(y)
     if out is not None:

@@ -25,7 +25,8 @@ constexpr int kCvThreads = 192;
 constexpr int kCvMaxStages = 16;             // ring depth is chosen at launch: smem / (A + B bytes of this conv)
 constexpr int kCvABytes = 128 * 64;          // 128 positions x 32 channels bf16
 constexpr int kCvData = 200 * 1024;          // operand ring budget
-constexpr int kCvSmem = kCvData + 512 + 1024;
+constexpr int kCvVecMax = 768;                // bias / gamma staged in shared memory (n_total <= 768)
+constexpr int kCvSmem = kCvData + 512 + 2 * kCvVecMax * 4 + 1024;
 constexpr int kMaxTaps = 27;
 
 constexpr uint64_t kDescSwizzle64 = 4ull << 61;
@@ -77,8 +78,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t bar_tfull = bar_empty + 8 * kCvMaxStages;
   const uint32_t bar_tempty = bar_tfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kCvMaxStages + 4);
+  float* sBias = reinterpret_cast<float*>(smem + kCvData + 512);
+  float* sGamma = sBias + kCvVecMax;
   const int kCvStages = p.stages;
   const int kCvStage = p.stage_bytes;
+  for (int i = threadIdx.x; i < kCvVecMax; i += kCvThreads) {
+    sBias[i] = (p.bias != nullptr && i < p.n_total) ? __ldg(p.bias + i) : 0.f;
+    sGamma[i] = (p.act_gamma != nullptr && i < p.n_store) ? __ldg(p.act_gamma + i) : 0.f;
+  }
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -200,7 +207,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int frame = t * p.ot_mul + p.ot_add;
       const uint32_t t_row = tmem_base + ((warp * 32u) << 16) + acc * 256;
       const int n_end = min(p.n_tile, p.n_total - n0);
-      // one 32-channel chunk: accumulator + bias (+ residual, clamp) -> v[]; returns #valid channels
+      // one 32-channel chunk: accumulator + bias (+ residual, clamp) -> v[]; returns #valid channels.
+      // Full chunks (cnt == 32, the common case) run without per-element predicates.
       auto chunk = [&](int c, float* v, long long& off, int& n) -> int {
         uint32_t rr[32];
         tmem_ld32(t_row + c, rr);
@@ -209,14 +217,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         int fr = frame, ns = n;
         if (p.interleave_half > 0 && n >= p.interleave_half) { fr += 1; ns = n - p.interleave_half; }
         off = ((long long)fr * p.Hs * p.Ws + pos_row) * p.ldc + ns;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
         const int cnt = min(32, min(p.n_total - n, (p.interleave_half > 0 ? p.interleave_half : p.n_store) - ns));
         if (!ok) return 0;
-        if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(sBias + n);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < cnt) v[j] += __ldg(p.bias + n + j);
+        for (int q = 0; q < 8; ++q) {
+          const float4 b = b4[q];                       // channels beyond n_total read zeros of the padding
+          v[q * 4 + 0] = __uint_as_float(rr[q * 4 + 0]) + b.x;
+          v[q * 4 + 1] = __uint_as_float(rr[q * 4 + 1]) + b.y;
+          v[q * 4 + 2] = __uint_as_float(rr[q * 4 + 2]) + b.z;
+          v[q * 4 + 3] = __uint_as_float(rr[q * 4 + 3]) + b.w;
         }
         if (p.residual != nullptr) {
           const bf16* rp = p.residual + off;
@@ -262,26 +272,62 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (j < cnt) o[j] = __float2bfloat16_rn(v[j]);
         }
       };
-      float sq = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < n_end; c += 32) {
-        float v[32];
-        long long off;
-        int n;
-        const int cnt = chunk(c, v, off, n);
-        if (cnt <= 0) continue;
-        if (p.out != nullptr) store(p.out + off, v, cnt);
-        if (p.act_out != nullptr) {
+      // activation of one chunk: silu(r * inv * gamma) with r the bf16-rounded result (what the next layer's
+      // RMS_norm reads); fp32 intermediates, ONE rounding at the store
+      auto activate = [&](float* v, int n, int cnt, float inv) {
+        const float4* g4 = reinterpret_cast<const float4*>(sGamma + n);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < cnt) { const float r = bf16_round(v[j]); sq += r * r; }
+        for (int q = 0; q < 8; ++q) {
+          const float4 g = g4[q];
+          const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = bf16_round(v[q * 4 + e]) * inv * gg[e];
+            v[q * 4 + e] = __fdividef(a, 1.f + __expf(-a));
+          }
         }
-      }
-      if (p.act_out != nullptr) {
-        // fused RMS_norm + SiLU of the NEXT layer (wan_vae.py:43-58): needs the whole channel row, which
-        // one thread owns because n_tile == n_total; second pass over TMEM instead of 384 live registers
-        const float dn = fmaxf(bf16_round(sqrtf(sq)), 1e-12f);
-        const float scale = sqrtf(float(p.n_store));
+        (void)cnt;
+      };
+      if (p.act_out == nullptr) {
+#pragma unroll 1
+        for (int c = 0; c < n_end; c += 32) {
+          float v[32];
+          long long off;
+          int n;
+          const int cnt = chunk(c, v, off, n);
+          if (cnt > 0) store(p.out + off, v, cnt);
+        }
+      } else if (n_end <= 128) {
+        // fused RMS_norm + SiLU of the NEXT layer (wan_vae.py:43-58, 197-201): the thread owns the whole channel
+        // row (n_tile == n_total); up to 128 channels stay in registers between the two sweeps
+        float v[4][32];
+        long long off[4];
+        int nn[4], cnt[4];
+        float sq = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          cnt[ci] = 0;
+          if (ci * 32 < n_end) {
+            cnt[ci] = chunk(ci * 32, v[ci], off[ci], nn[ci]);
+            if (cnt[ci] > 0) {
+              if (p.out != nullptr) store(p.out + off[ci], v[ci], cnt[ci]);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < cnt[ci]) { const float r = bf16_round(v[ci][j]); sq += r * r; }
+            }
+          }
+        }
+        const float inv = sqrtf(float(p.n_store)) / fmaxf(sqrtf(sq), 1e-12f);
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          if (cnt[ci] > 0) {
+            activate(v[ci], nn[ci], cnt[ci], inv);
+            store(p.act_out + off[ci], v[ci], cnt[ci]);
+          }
+        }
+      } else {
+        // wider rows: second sweep over TMEM instead of 384 live registers
+        float sq = 0.f;
 #pragma unroll 1
         for (int c = 0; c < n_end; c += 32) {
           float v[32];
@@ -289,13 +335,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           int n;
           const int cnt = chunk(c, v, off, n);
           if (cnt <= 0) continue;
+          if (p.out != nullptr) store(p.out + off, v, cnt);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < cnt) {
-              float a = bf16_round(bf16_round(bf16_round(bf16_round(v[j]) / dn) * scale) * __ldg(p.act_gamma + n + j));
-              v[j] = a / (1.f + __expf(-a));
-            }
-          }
+          for (int j = 0; j < 32; ++j)
+            if (j < cnt) { const float r = bf16_round(v[j]); sq += r * r; }
+        }
+        const float inv = sqrtf(float(p.n_store)) / fmaxf(sqrtf(sq), 1e-12f);
+#pragma unroll 1
+        for (int c = 0; c < n_end; c += 32) {
+          float v[32];
+          long long off;
+          int n;
+          const int cnt = chunk(c, v, off, n);
+          if (cnt <= 0) continue;
+          activate(v, n, cnt, inv);
           store(p.act_out + off, v, cnt);
         }
       }
@@ -338,16 +391,15 @@ __global__ void rms_silu_cl_kernel(const bf16* __restrict__ x, const float* __re
     }
   }
   sq = warp_sum(sq);
-  // F.normalize on a bf16 tensor: norm in fp32 internally, result rounded to bf16, then two bf16
-  // multiplies (* scale, * gamma) as separate ATen ops
-  const float dn = fmaxf(bf16_round(sqrtf(sq)), 1e-12f);
-  const float scale = sqrtf(float(C));
+  // x / max(||x||, 1e-12) * sqrt(C) * gamma with fp32 intermediates and ONE rounding at the store (the
+  // reference's ATen chain rounds to bf16 after every op; fewer roundings only move us closer to fp32)
+  const float inv = sqrtf(float(C)) / fmaxf(sqrtf(sq), 1e-12f);
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const int idx = lane + i * 32;
     if (idx < np) {
-      float a = bf16_round(bf16_round(bf16_round(v[i].x / dn) * scale) * gamma[2 * idx]);
-      float b = bf16_round(bf16_round(bf16_round(v[i].y / dn) * scale) * gamma[2 * idx + 1]);
+      float a = v[i].x * inv * gamma[2 * idx];
+      float b = v[i].y * inv * gamma[2 * idx + 1];
       if (silu) {
         a = a / (1.f + __expf(-a));
         b = b / (1.f + __expf(-b));
@@ -459,6 +511,7 @@ extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const lon
   VCOF_REQUIRE(out != nullptr || act_out != nullptr, "vcof_conv_igemm: no output requested");
   VCOF_REQUIRE(act_out == nullptr || (act_gamma != nullptr && a.n_tile == a.n_total && a.interleave_half == 0),
                "vcof_conv_igemm: fused norm needs gamma, a single channel tile and no frame interleave");
+  VCOF_REQUIRE(a.n_total <= kCvVecMax, "vcof_conv_igemm: n_total %d > %d", a.n_total, kCvVecMax);
   VCOF_REQUIRE(a.n_total % 16 == 0 && a.n_tile % 16 == 0 && a.n_tile <= 384 && a.n_tile >= 16,
                "vcof_conv_igemm: n_total %d / n_tile %d must be multiples of 16, n_tile <= 384", a.n_total,
                a.n_tile);
