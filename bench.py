@@ -34,6 +34,8 @@ WORKLOADS = {
     # name: (dit config, latent [C,f,h,w], frame_split, n_ctx tokens)
     "c2": (dict(dim=5120, ffn_dim=13824, num_heads=40, num_layers=40), (16, 21, 90, 160), 10, 77),
     "c1": (dict(dim=1536, ffn_dim=8960, num_heads=12, num_layers=30), (16, 5, 32, 32), 2, 77),
+    # BASELINE.json configs[4]: 321 frames (4x length extrapolation) x 720p, meant for 8 GPUs
+    "c5": (dict(dim=5120, ffn_dim=13824, num_heads=40, num_layers=40), (16, 81, 90, 160), 40, 77),
 }
 METRIC = "denoising_steps_per_sec"
 

@@ -30,7 +30,8 @@ def main():
             torch.nn.init.normal_(p, std=1.0 / (p[0].numel() ** 0.5))
     vae = vae.to(dev, torch.bfloat16).eval()
     res = {}
-    for name, shape in (("small", (1, 16, 5, 6, 10)), ("720p", (1, 16, 6, 90, 160))):
+    cases = [("small", (1, 16, max(5, 2 * world + 1), 6, 10)), ("720p", (1, 16, max(6, 21 if world >= 4 else 6), 90, 160))]
+    for name, shape in cases:
         g = torch.Generator().manual_seed(1)
         z = torch.randn(*shape, generator=g).bfloat16().to(dev)
         with torch.no_grad():
