@@ -281,12 +281,14 @@ def run_vcof(args):
 
     # ---- whole pipeline through WanPipeline.__call__ (VAE encode -> 4 steps -> VAE decode x2), host in/out
     pipe_stats = None
-    if world == 1 and not args.no_pipeline:
+    if not args.no_pipeline and args.workload != "c5":
         from videocof_b200.pipeline import WanPipeline
         from videocof_b200.vae import AutoencoderKLWan
         torch.manual_seed(2)
         vae = AutoencoderKLWan().to(dev, torch.bfloat16).eval()
         pipe = WanPipeline(None, None, vae, model, sched)
+        if world > 1:
+            vae.enable_temporal_sharding()          # the DiT is already sequence-parallel (see above)
         src_frames = 4 * fs - 3                                   # fs latent frames of source video
         H, W = lat[2] * 8, lat[3] * 8
         video_host = (torch.rand(1, 3, src_frames, H, W, generator=g) * 2 - 1).to(torch.bfloat16).pin_memory()
@@ -298,16 +300,17 @@ def run_vcof(args):
                         shift=3, repeat_rope=True, cot=True, generator=gen)
 
         run_pipe()                                                # warm-up (allocator, weight packs)
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         out = run_pipe()
-        torch.cuda.synchronize()
+        barrier()
         dt = time.perf_counter() - t0
         n_edit = int(out.edit_videos.shape[2])
         pipe_stats = {"seconds": dt, "frames_per_sec": n_edit / dt, "edit_frames": n_edit,
                       "ground_frames": int(out.ground_videos.shape[2]), "source_frames": src_frames,
                       "what": "WanPipeline.__call__: VAE encode(source, host bf16) + 4 DiT steps + VAE decode(ground) + "
-                              "VAE decode(edit) -> fp32 numpy frames on the host; random-init weights"}
+                              "VAE decode(edit) -> fp32 numpy frames on the host; random-init weights"
+                              + ("; DiT token-sharded, VAE frame-sharded with halos" if world > 1 else "")}
         del vae, pipe, out
 
     if rank != 0:

@@ -93,3 +93,23 @@ def test_vae_temporal_sharding_matches_unsharded(world, frames, model, monkeypat
     assert rel < 3e-2, rel
     assert float((got.float() - ref.float()).abs().max()) < 0.1
     assert all(len(m) == 0 for m in mailbox[:-1])
+
+
+@pytest.mark.parametrize("world,frames", [(2, 17), (3, 25), (2, 13)])
+def test_vae_temporal_sharding_encode_matches_unsharded(world, frames, model, monkeypatch):
+    """Encoder side: per-rank video ranges on the reference's (1,4,4,...) chunk boundaries, stride-2 temporal
+    convolutions across the rank boundary."""
+    vcof_emulator.install(monkeypatch)
+    g = torch.Generator().manual_seed(4)
+    video = (torch.rand(1, 3, frames, 16, 16, generator=g) * 2 - 1).bfloat16()
+    with torch.no_grad():
+        ref = model.model.encode(video, model.scale)[0]
+        mailbox = [[] for _ in range(world)]
+        outs = [None] * world
+        for r in range(world):
+            model.model.encode(video, model.scale, shard=_FakeShard(r, world, mailbox, outs))
+    got = torch.cat(outs, dim=1)
+    assert got.shape == ref.shape
+    rel = float((got[:16].float() - ref[:16].float()).norm() / ref[:16].float().norm())
+    assert rel < 3e-2, rel
+    assert all(len(m) == 0 for m in mailbox[:-1])

@@ -50,10 +50,20 @@ def main():
             torch.cuda.synchronize()
             t_shard = time.perf_counter() - t0
             vae._shard = None
-        diff = float((out.float() - ref.float()).abs().max())
+            # encoder: video of the decoded length (1 + 4k frames)
+            vid = ref.clamp(-1, 1)
+            vae._shard = None
+            mu_ref = vae.encode(vid)[0].mode()
+            vae.enable_temporal_sharding()
+            mu = vae.encode(vid)[0].mode()
+            torch.cuda.synchronize()
+            vae._shard = None
+        enc_diff = float((mu.float() - mu_ref.float()).abs().max())
+        diff = max(float((out.float() - ref.float()).abs().max()), enc_diff)
         d = torch.tensor([diff], device=dev)
         dist.all_reduce(d, op=dist.ReduceOp.MAX)
-        res[name] = dict(shape=list(out.shape), max_abs_diff=float(d), single_ms=t_single * 1e3, sharded_ms=t_shard * 1e3)
+        res[name] = dict(shape=list(out.shape), latent=list(mu.shape), max_abs_diff=float(d),
+                         decode_single_ms=t_single * 1e3, decode_sharded_ms=t_shard * 1e3)
     if rank == 0:
         ok = all(v["max_abs_diff"] == 0.0 for v in res.values())
         print(json.dumps({"vae_shard_check": "ok" if ok else "FAIL", "world": world, **res}))

@@ -70,6 +70,14 @@ class WanPipeline:
     def maybe_free_model_hooks(self):
         pass
 
+    def enable_multi_gpus(self, group=None):
+        """One call for a multi-GPU box (one process per GPU, torch.distributed initialised): token-sharded DiT with a
+        K/V all-gather per layer (videocof_b200.dist) and frame-sharded VAE with 2-frame halos (vae.TimeShard).  Every
+        rank must call the pipeline with the same inputs / seeds and receives the full result."""
+        self.transformer.enable_multi_gpus_inference(group)
+        self.vae.enable_temporal_sharding(group)
+        return self
+
     def enable_model_cpu_offload(self, gpu_id=None, device="cuda", **_):
         """The CLIs default to offload modes sized for 24-80 GB GPUs (fast_infer.py:136, :348-361).  A fused path
         that reads weight pointers directly cannot be paged by accelerate hooks, and a B200 holds the whole

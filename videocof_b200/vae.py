@@ -433,15 +433,37 @@ def downsample(x, rs):
     n_total = pw.shape[1]
     y = _alloc(T, H2, W2, n_total, x.device)
     ops.conv_igemm(x, dims, strides, pw, taps, cin_p, _geom(T, H2, W2, n_total, _ntile(n_total)), pb, y)
-    if rs.mode == "downsample3d" and T > 1:
+    first = _SHARD is None or _SHARD.rank == 0
+    if rs.mode == "downsample3d" and (T > 1 or not first):
         tw, tb, tcin, ttg = pack_conv(rs.time_conv)
-        To = (T - 1) // 2
-        z = _alloc(1 + To, H2, W2, n_total, x.device)
-        z[0].copy_(y[0])
-        d5, s5 = _view5(y)
-        ttaps = [(0, 0, 0, 0, a) for a in range(3)]
-        ops.conv_igemm(y, d5, s5, tw, ttaps, tcin, _geom(To, H2, W2, n_total, _ntile(n_total), ot=(1, 1), t_stride=2),
-                       tb, z, tgroup=ttg)
+        if _SHARD is None:
+            To = (T - 1) // 2
+            z = _alloc(1 + To, H2, W2, n_total, x.device)
+            z[0].copy_(y[0])
+            d5, s5 = _view5(y)
+            ttaps = [(0, 0, 0, 0, a) for a in range(3)]
+            ops.conv_igemm(y, d5, s5, tw, ttaps, tcin,
+                           _geom(To, H2, W2, n_total, _ntile(n_total), ot=(1, 1), t_stride=2), tb, z, tgroup=ttg)
+        else:
+            # out[1+m] = conv(y[2m], y[2m+1], y[2m+2]) on GLOBAL frame indices; ownership follows the reference's
+            # (1, 4, 4, ...) chunking, so a rank > 0 owns an even number of frames and needs exactly the last
+            # frame of its left neighbour (second halo slot); rank 0 keeps frame 0 as is.
+            yh = _haloed(y)
+            _SHARD.exchange(yh)
+            if first:
+                To = (T - 1) // 2
+                z = _alloc(1 + To, H2, W2, n_total, x.device)
+                z[0].copy_(y[0])
+                shift, ot = 2, (1, 1)
+            else:
+                To = T // 2
+                z = _alloc(To, H2, W2, n_total, x.device)
+                shift, ot = 1, (1, 0)
+            d5, s5 = _view5(yh)
+            ttaps = [(0, 0, 0, 0, a + shift) for a in range(3)]
+            if To > 0:
+                ops.conv_igemm(yh, d5, s5, tw, ttaps, tcin,
+                               _geom(To, H2, W2, n_total, _ntile(n_total), ot=ot, t_stride=2), tb, z, tgroup=ttg)
         y = z
     return y
 
@@ -544,28 +566,54 @@ class AutoencoderKLWan_(nn.Module):
                 raise VcofError(f"unexpected layer {type(layer)}")
         return x, x_act
 
-    def encode(self, x, scale):
-        """x [1, 3, T, H, W] -> [1, 2*z, f, H/8, W/8] = cat(normalised mu, logvar) (:520-548)."""
+    def encode(self, x, scale, shard=None):
+        """x [1, 3, T, H, W] -> [1, 2*z, f, H/8, W/8] = cat(normalised mu, logvar) (:520-548).
+
+        shard: optional TimeShard — rank r encodes the video frames of its latent-frame range (frame 0 alone, then 4
+        per latent: the reference's own chunk boundaries) with 2-frame halos; the latents are all-gathered."""
+        global _SHARD
         self._check(x)
         if x.shape[0] != 1:
             raise VcofError("encode expects batch 1 (the reference loops over the batch, :647-653)")
         if (x.shape[2] - 1) % 4 != 0 or x.shape[3] % 8 or x.shape[4] % 8:
             raise VcofError("video must have 1+4k frames and H, W multiples of 8")
         enc = self.encoder
-        h = ops.nchw_to_cl(x[0].to(torch.bfloat16).contiguous(), 32)
-        h = conv_causal(h, enc.conv1)
-        h, a = self._run(h, enc.downsamples)
-        h, a = self._run(h, enc.middle, a, tail_norm=enc.head[0])
-        if a is None:
-            a = rms_silu(h, enc.head[0])
-        h = conv_causal(a, enc.head[2])                        # [f, h, w, 32]
+        T = x.shape[2]
+        f = (T - 1) // 4 + 1
+        sharded = shard is not None and shard.world > 1 and f >= 2 * shard.world
+        xv = x[0].to(torch.bfloat16)
+        if sharded:
+            base, extra = divmod(f, shard.world)
+            sizes = [base + (1 if r < extra else 0) for r in range(shard.world)]
+            a0 = sum(sizes[:shard.rank])
+            b0 = a0 + sizes[shard.rank]
+            t0, t1 = (0 if a0 == 0 else 4 * a0 - 3), 4 * b0 - 3
+            xv = xv[:, t0:t1]
+        h = ops.nchw_to_cl(xv.contiguous(), 32)
+        if sharded:
+            _SHARD = shard
+            own = _alloc(*h.shape, h.device)
+            own.copy_(h)
+            h = own
+        try:
+            h = conv_causal(h, enc.conv1)
+            h, a = self._run(h, enc.downsamples)
+            h, a = self._run(h, enc.middle, a, tail_norm=enc.head[0])
+            if a is None:
+                a = rms_silu(h, enc.head[0])
+            h = conv_causal(a, enc.head[2])                        # [f_r, h, w, 32]
+        finally:
+            _SHARD = None
         h = conv1x1(h, self.conv1)
         z = self.z_dim
         mean = scale[0].to(x.device, torch.bfloat16).float().contiguous()
         inv_std = scale[1].to(x.device, torch.bfloat16).float().contiguous()
         mu = ops.cl_to_nchw(h, z, sub=mean, mul=inv_std)
         logvar = ops.cl_to_nchw(h[..., z:], z)
-        return torch.cat([mu, logvar], dim=0)[None]
+        out = torch.cat([mu, logvar], dim=0)                       # [2z, f_r, h, w]
+        if sharded:
+            out = shard.gather_frames(out, sizes)
+        return out[None]
 
     def decode(self, z, scale, shard=None):
         """z [1, 16, f, h, w] (normalised) -> [1, 3, 4(f-1)+1, 8h, 8w] (:550-575); clamp is applied by the caller
@@ -677,16 +725,17 @@ class AutoencoderKLWan(nn.Module):
         return self.model.conv1.weight.device
 
     def _encode(self, x):
-        return torch.cat([self.model.encode(u.unsqueeze(0), self.scale) for u in x], dim=0)
+        shard = getattr(self, "_shard", None)
+        return torch.cat([self.model.encode(u.unsqueeze(0), self.scale, shard=shard) for u in x], dim=0)
 
     def encode(self, x, return_dict=True):
         posterior = DiagonalGaussianDistribution(self._encode(x))
         return AutoencoderKLOutput(latent_dist=posterior) if return_dict else (posterior,)
 
     def enable_temporal_sharding(self, group=None):
-        """Decode with the frames sharded over the ranks of `group` (default WORLD): 2-frame halo exchange per
-        causal convolution (TimeShard); single-rank behaviour is unchanged.  Clips with fewer than two latent
-        frames per rank (e.g. the 1-latent grounding segment) are decoded redundantly on every rank."""
+        """Encode / decode with the frames sharded over the ranks of `group` (default WORLD): 2-frame halo exchange
+        per causal convolution (TimeShard); single-rank behaviour is unchanged.  Clips with fewer than two latent
+        frames per rank (e.g. the 1-latent grounding segment) are processed redundantly on every rank."""
         self._shard = TimeShard(group)
 
     def _decode(self, zs):
