@@ -94,10 +94,13 @@ int vcof_linear_f32(const float* x, const void* w, const void* bias, float* out,
  *   taps[5*i..]  (c_base, dw, p, dh, dt): coordinate offsets of tap i added to the tile origin; taps come in groups
  *                of `tgroup` (1 or 3) consecutive entries that differ only by dt, dt+1, dt+2 — one TMA box with a
  *                t-extent of tgroup feeds the whole group (the TMA unit's cost is per box)
- *   w            bf16 [k_total/32, n_total, 32]: slice ((group * cin/32 + chunk) * tgroup + j) holds the 32 input
- *                channels `chunk` of tap (group, j) for every output channel (n_total padded to a multiple of 16)
- *   geom[16]     T_out, H_out, W_out, t_stride, n_total, n_tile, ot_mul, ot_add, oh_mul, oh_add, ow_mul,
- *                ow_add, Hs, Ws, interleave_half, n_store — output position (t,h,w) is stored at
+ *   w            bf16 [k_total/kc, n_total, kc]: slice ((group * cin/kc + chunk) * tgroup + j) holds the kc input
+ *                channels `chunk` of tap (group, j) for every output channel (n_total padded to a multiple of 16);
+ *                cin is the per-tap K extent, zero-padded in the weights to a multiple of kc (the activation box may
+ *                read past the tensor's channels: TMA zero-fills, or the zero weights cancel a neighbour's data)
+ *   geom[17]     T_out, H_out, W_out, t_stride, n_total, n_tile, ot_mul, ot_add, oh_mul, oh_add, ow_mul,
+ *                ow_add, Hs, Ws, interleave_half, n_store, kc (32 | 64 channels per K slice = 64 | 128-byte TMA
+ *                rows; 64 whenever the layer has >= 64 input channels) — output position (t,h,w) is stored at
  *                [t*ot_mul+ot_add, h*oh_mul+oh_add, w*ow_mul+ow_add] of a [*, Hs, Ws, ldc] tensor;
  *                interleave_half > 0 sends channels >= half to the next frame (upsample3d, wan_vae.py:137-141)
  *   bias fp32 [n_total] | NULL;  residual bf16 (same addressing as out) | NULL;  clamp > 0 clamps.
@@ -136,12 +139,14 @@ int vcof_softmax_rows(const float* s, long long lds, void* p, long long ldp, int
  * Pins the descriptor conventions the GEMM / attention kernels depend on. */
 int vcof_debug_umma_probe(const void* a, const void* b, float* d, int mode, void* stream);
 
-/* Sustained TMA box-load rate: every CTA streams `iters` boxes of the given rank-2 / rank-5 bf16 view through an
- * 8-deep shared-memory ring (no compute); cycles[cta] receives the elapsed SM clocks.  Explains the feed-rate
+/* Sustained TMA box-load rate: in every CTA `producers` (1..4) lanes of different warps each stream `iters` boxes of
+ * the given rank-2 / rank-5 bf16 view through their own shared-memory ring (~192 KB in flight in total, no compute);
+ * cycles[cta] receives the elapsed SM clocks.  flags: bits 0-3 boxes per barrier round trip (0 = 1), bit 4 alternate two
+ * copies of the tensor map, bit 5 poll with mbarrier.test_wait instead of try_wait.  Explains the feed-rate
  * ceilings quoted in profiles/ (rows of 64 B vs 128 B, strided pixel slices vs contiguous rows). */
 int vcof_debug_tma_probe(const void* base, int rank, const long long* dims, const long long* strides, const int* box,
                          int swizzle_bytes, int iters, const int* coords, int step_dim, int step, int wrap,
-                         unsigned long long* cycles, int grid, void* stream);
+                         unsigned long long* cycles, int grid, int producers, int flags, void* stream);
 
 #ifdef __cplusplus
 }

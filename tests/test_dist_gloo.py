@@ -1,5 +1,5 @@
 """Sequence-parallel plumbing (videocof_b200.dist) on CPU with gloo, world_size 2 and 3: token sharding with
-padding, K/V all-gather, local-query attention, row gather — against un-sharded attention.  The attention
+padding, K/V all-gather or head exchange (all-to-all), attention, row gather — against un-sharded attention.  The attention
 function is injected (the libvcof kernel needs a GPU; the math here is the oracle's attention_ref)."""
 import os
 import socket
@@ -29,13 +29,13 @@ def _attn(q, k, v, heads, kv_len=None, out=None, **_):
     return o
 
 
-def _worker(rank, world, port, L, q):
+def _worker(rank, world, port, L, q, mode="gather"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from videocof_b200.dist import SequenceParallel
         torch.manual_seed(0)
-        heads, d = 2, 16
+        heads, d = (2, 16) if mode == "gather" else (2 * world, 8)
         C = heads * d
         seq_len = (L + world - 1) // world * world              # reference padding rule (:904-905)
         full = [torch.randn(seq_len, C) for _ in range(3)]
@@ -45,7 +45,13 @@ def _worker(rank, world, port, L, q):
         rows = seq_len // world
         sp.configure(kv_len=L, rows=rows)
         ql, kl, vl = (sp.shard(t) for t in full)
-        out_local = sp.attention(ql.contiguous(), kl.contiguous(), vl.contiguous(), heads)
+        if mode == "gather":
+            out_local = sp.attention(ql.contiguous(), kl.contiguous(), vl.contiguous(), heads)
+        else:
+            assert sp.can_exchange_heads(heads)
+            for name, t in (("q", ql), ("k", kl), ("v", vl)):
+                sp.start_exchange(name, t.contiguous())
+            out_local = sp.attention_exchanged(heads, out=torch.empty(rows, C))
         gathered = sp.all_gather_rows(out_local)
         ref = _attn(full[0], full[1], full[2], heads, kv_len=L)
         err = float((gathered[:L] - ref[:L]).abs().max())
@@ -54,12 +60,13 @@ def _worker(rank, world, port, L, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,L", [(2, 37), (3, 50), (2, 64)])
-def test_sequence_parallel_attention_matches_unsharded(world, L):
+@pytest.mark.parametrize("world,L,mode", [(2, 37, "gather"), (3, 50, "gather"), (2, 64, "gather"),
+                                           (2, 37, "heads"), (3, 50, "heads")])
+def test_sequence_parallel_attention_matches_unsharded(world, L, mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, L, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, L, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]

@@ -48,9 +48,12 @@ CONV_CASES = {
 }
 
 
+@pytest.mark.parametrize("kc", ["32", "64"])
 @pytest.mark.parametrize("name", list(CONV_CASES))
-def test_conv_igemm_vs_contract(name):
+def test_conv_igemm_vs_contract(name, kc, monkeypatch):
+    """Both K-slice widths of the kernel (64- and 128-byte TMA rows, SW64 / SW128 descriptors)."""
     from videocof_b200 import vae
+    monkeypatch.setenv("VCOF_CONV_KC", kc)
     c = CONV_CASES[name]
     torch.manual_seed(0)
     conv = vae.CausalConv3d(c["cin"], c["cout"], c["k"], padding=tuple(k // 2 for k in c["k"]))

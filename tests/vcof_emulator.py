@@ -32,12 +32,13 @@ def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=Non
     store = x.untyped_storage()
     full = torch.empty(0, dtype=x.dtype).set_(store)          # whole storage as a flat tensor
     acc = torch.zeros(T, H, W, n_total)
-    ccn = cin // 32
+    kc = w.shape[2]                                    # channels per K slice (32 or 64)
+    ccn = cin // kc
     assert len(taps) % tgroup == 0
     for g0 in range(0, len(taps), tgroup):            # contract: group members differ only by consecutive dt
         for j in range(1, tgroup):
             assert taps[g0 + j][:4] == taps[g0][:4] and taps[g0 + j][4] == taps[g0][4] + j
-    w5 = w.float().view(len(taps) // tgroup, ccn, tgroup, n_total, 32)   # [G, cc, tg, n, 32]
+    w5 = w.float().view(len(taps) // tgroup, ccn, tgroup, n_total, kc)   # [G, cc, tg, n, kc]
     tt, hh, ww = torch.meshgrid(torch.arange(T), torch.arange(H), torch.arange(W), indexing="ij")
     cc = torch.arange(cin)
     for i, (c_base, dw, p, dh, dt) in enumerate(taps):

@@ -29,7 +29,7 @@ SIGNATURES = {
     "vcof_cl_to_nchw": [c_void_p, c_ll, c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p],
     "vcof_softmax_rows": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_float, c_void_p],
     "vcof_debug_tma_probe": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
-                             c_int, c_void_p, c_int, c_void_p],
+                             c_int, c_void_p, c_int, c_int, c_int, c_void_p],
     "vcof_debug_umma_probe": [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "vcof_linear_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                         c_void_p],

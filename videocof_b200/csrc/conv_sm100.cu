@@ -23,7 +23,7 @@ namespace vcof {
 
 constexpr int kCvThreads = 192;
 constexpr int kCvMaxStages = 16;             // ring depth is chosen at launch: smem / (A + B bytes of this conv)
-constexpr int kCvABytes = 128 * 64;          // 128 positions x 32 channels bf16
+constexpr int kCvRows = 128;                 // positions per tile (= TMEM lanes)
 constexpr int kCvData = 200 * 1024;          // operand ring budget
 constexpr int kCvVecMax = 768;                // bias / gamma staged in shared memory (n_total <= 768)
 constexpr int kCvSmem = kCvData + 512 + 2 * kCvVecMax * 4 + 1024;
@@ -43,8 +43,11 @@ struct ConvTap {
 
 struct ConvArgs {
   ConvTap taps[kMaxTaps];
-  int ntaps, cin_chunks;      // K loop = ntaps x cin_chunks slices of 32 channels
-  int cin;                    // padded input channels (multiple of 32): weight K stride per tap
+  int ntaps, cin_chunks;      // K loop = ntaps x cin_chunks slices of kc channels
+  int cin;                    // padded input channels (multiple of kc): weight K stride per tap
+  int kc;                     // channels per slice: 64 (128-byte rows, SW128) or 32 (64-byte rows, SW64).  The TMA
+                              // unit's cost is per box ROW (profiles/r1_tma_probe.txt), so rows should be 128 B
+                              // whenever the layer has >= 64 input channels
   int T_out, H_out, W_out;    // logical output grid the tiles walk over
   int t_stride;               // t_in = t_out * t_stride + dt
   int n_total, n_tile;        // output channels (padded to 16) and channels per CTA tile (<= 384)
@@ -121,7 +124,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int nacc = (p.n_tile <= 256) ? 2 : 1;            // accumulator buffers in TMEM
   const int nsub = (p.n_tile <= 256) ? 1 : 2;            // MMAs per k-step (N <= 256 each)
   const int n_sub = p.n_tile / nsub;
-  const uint32_t b_bytes = p.n_tile * 64;
+  const uint32_t row_bytes = p.kc * 2;
+  const uint32_t a_bytes = kCvRows * row_bytes;
+  const uint32_t b_bytes = p.n_tile * row_bytes;
 
   auto decode = [&](int tile, int& t, int& h0, int& w0, int& n0) {
     int nt = tile % n_tiles;
@@ -144,14 +149,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const ConvTap tp = p.taps[g * p.tgroup];            // first tap of the group (lowest dt)
           for (int cc = 0; cc < p.cin_chunks; ++cc) {
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            mbar_expect_tx(bar_full + 8 * s, p.tgroup * (kCvABytes + b_bytes));
+            mbar_expect_tx(bar_full + 8 * s, p.tgroup * (a_bytes + b_bytes));
             uint8_t* st = smem + s * kCvStage;
-            // [32 c, 16 w, 1, 8 h, tgroup t] -> tgroup consecutive 128x64B K-major tiles
-            tma_load_5d(smem_u32(st), &tmX, bar_full + 8 * s, tp.c_base + cc * 32, w0 + tp.dw, tp.p, h0 + tp.dh,
+            // [kc c, 16 w, 1, 8 h, tgroup t] -> tgroup consecutive 128-row K-major tiles
+            tma_load_5d(smem_u32(st), &tmX, bar_full + 8 * s, tp.c_base + cc * p.kc, w0 + tp.dw, tp.p, h0 + tp.dh,
                         t * p.t_stride + tp.dt);
             const int slice = (g * p.cin_chunks + cc) * p.tgroup;
             for (int j = 0; j < nsub; ++j)
-              tma_load_3d(smem_u32(st + p.tgroup * kCvABytes + j * p.tgroup * n_sub * 64), &tmW, bar_full + 8 * s, 0,
+              tma_load_3d(smem_u32(st + p.tgroup * a_bytes + j * p.tgroup * n_sub * row_bytes), &tmW, bar_full + 8 * s, 0,
                           n0 + j * n_sub, slice);
             if (++s == kCvStages) { s = 0; ph ^= 1; }
           }
@@ -161,6 +166,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   } else if (warp == 5) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, n_sub, false, false);
+      const bool wide = p.kc == 64;
+      const int ksteps = p.kc / 16;
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -174,15 +181,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
           const uint32_t a_stage = smem_u32(smem + s * kCvStage);
-          const uint32_t b_stage = a_stage + p.tgroup * kCvABytes;
+          const uint32_t b_stage = a_stage + p.tgroup * a_bytes;
           for (int dt = 0; dt < p.tgroup; ++dt) {
-            const uint32_t a_base = a_stage + dt * kCvABytes;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              for (int j = 0; j < nsub; ++j)
-                umma_ss(d_tmem + j * n_sub, make_desc_kmajor_sw64(a_base + ks * 32),
-                        make_desc_kmajor_sw64(b_stage + (j * p.tgroup + dt) * n_sub * 64 + ks * 32), idesc,
+            const uint32_t a_base = a_stage + dt * a_bytes;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              for (int j = 0; j < nsub; ++j) {
+                const uint32_t a_addr = a_base + ks * 32;
+                const uint32_t b_addr = b_stage + (j * p.tgroup + dt) * n_sub * row_bytes + ks * 32;
+                umma_ss(d_tmem + j * n_sub, wide ? make_desc_kmajor_sw128(a_addr) : make_desc_kmajor_sw64(a_addr),
+                        wide ? make_desc_kmajor_sw128(b_addr) : make_desc_kmajor_sw64(b_addr), idesc,
                         (k | dt | ks) != 0);
+              }
             }
           }
           umma_commit(bar_empty + 8 * s);
@@ -481,10 +490,12 @@ extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const lon
                                long long ldc, float clamp, void* act_out, const float* act_gamma,
                                void* stream) {
   // x_dims[5]: (c_inner, W, P, H, T) of the (parity-)view; x_strides[4]: element strides of dims 1..4
-  // geom[14]: T_out,H_out,W_out,t_stride,n_total,n_tile,ot_mul,ot_add,oh_mul,oh_add,ow_mul,ow_add,Hs,Ws
-  //           then [14] interleave_half, [15] n_store
+  // geom[17]: T_out,H_out,W_out,t_stride,n_total,n_tile,ot_mul,ot_add,oh_mul,oh_add,ow_mul,ow_add,Hs,Ws
+  //           then [14] interleave_half, [15] n_store, [16] kc (channels per K slice: 32 or 64)
   VCOF_REQUIRE(ntaps >= 1 && ntaps <= kMaxTaps, "vcof_conv_igemm: ntaps %d outside [1,%d]", ntaps, kMaxTaps);
-  VCOF_REQUIRE(cin % 32 == 0 && cin > 0, "vcof_conv_igemm: cin %d must be a positive multiple of 32", cin);
+  const int kc = geom[16];
+  VCOF_REQUIRE(kc == 32 || kc == 64, "vcof_conv_igemm: slice width %d must be 32 or 64", kc);
+  VCOF_REQUIRE(cin % kc == 0 && cin > 0, "vcof_conv_igemm: cin %d must be a positive multiple of %d", cin, kc);
   ConvArgs a;
   for (int i = 0; i < ntaps; ++i) {
     a.taps[i].c_base = taps[i * 5 + 0];
@@ -495,7 +506,8 @@ extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const lon
   }
   a.ntaps = ntaps;
   a.cin = cin;
-  a.cin_chunks = cin / 32;
+  a.cin_chunks = cin / kc;
+  a.kc = kc;
   a.T_out = geom[0]; a.H_out = geom[1]; a.W_out = geom[2]; a.t_stride = geom[3];
   a.n_total = geom[4]; a.n_tile = geom[5];
   a.ot_mul = geom[6]; a.ot_add = geom[7]; a.oh_mul = geom[8]; a.oh_add = geom[9];
@@ -524,7 +536,7 @@ extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const lon
                    "vcof_conv_igemm: taps of group %d must differ only by consecutive dt", g);
     }
   a.tgroup = tgroup;
-  a.stage_bytes = tgroup * (kCvABytes + a.n_tile * 64);      // multiples of 1 KB keep the SW64 tiles aligned
+  a.stage_bytes = tgroup * (kCvRows + a.n_tile) * kc * 2;    // multiples of 1 KB keep the swizzled tiles aligned
   a.stages = kCvData / a.stage_bytes;
   VCOF_REQUIRE(a.stages >= 2, "vcof_conv_igemm: stage of %d bytes leaves no ring", a.stage_bytes);
   if (a.stages > kCvMaxStages) a.stages = kCvMaxStages;
@@ -534,15 +546,15 @@ extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const lon
   uint64_t dims[5], strides[4];
   for (int i = 0; i < 5; ++i) dims[i] = (uint64_t)x_dims[i];
   for (int i = 0; i < 4; ++i) strides[i] = (uint64_t)x_strides[i] * 2;
-  const uint32_t box[5] = {32, 16, 1, 8, (uint32_t)tgroup};
-  int rc = make_tmap_nd_bf16(&tmX, x, 5, dims, strides, box, 64);
+  const uint32_t box[5] = {(uint32_t)kc, 16, 1, 8, (uint32_t)tgroup};
+  int rc = make_tmap_nd_bf16(&tmX, x, 5, dims, strides, box, kc * 2);
   if (rc) return rc;
   const int nsub = a.n_tile <= 256 ? 1 : 2;
-  // weights: [slices, n_total, 32] with slice = ((tap_group * cin_chunks + chunk) * tgroup + j)
-  uint64_t wd[3] = {32, (uint64_t)a.n_total, (uint64_t)(k_total / 32)};
-  uint64_t ws[2] = {64, (uint64_t)a.n_total * 64};
-  uint32_t wb[3] = {32, (uint32_t)(a.n_tile / nsub), (uint32_t)tgroup};
-  rc = make_tmap_nd_bf16(&tmW, w, 3, wd, ws, wb, 64);
+  // weights: [slices, n_total, kc] with slice = ((tap_group * cin_chunks + chunk) * tgroup + j)
+  uint64_t wd[3] = {(uint64_t)kc, (uint64_t)a.n_total, (uint64_t)(k_total / kc)};
+  uint64_t ws[2] = {(uint64_t)kc * 2, (uint64_t)a.n_total * kc * 2};
+  uint32_t wb[3] = {(uint32_t)kc, (uint32_t)(a.n_tile / nsub), (uint32_t)tgroup};
+  rc = make_tmap_nd_bf16(&tmW, w, 3, wd, ws, wb, kc * 2);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {

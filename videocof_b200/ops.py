@@ -235,7 +235,8 @@ def _arr(ctype, vals):
 def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=None, clamp=0.0, act_out=None,
                act_gamma=None, tgroup=1):
     """Raw binding of vcof_conv_igemm (see include/vcof.h).  x: any bf16 CUDA tensor whose storage the
-    5-D view (x_dims / x_strides, elements) addresses from x.data_ptr(); w: packed [slices, n_total, 32]."""
+    5-D view (x_dims / x_strides, elements) addresses from x.data_ptr(); w: packed [slices, n_total, kc] with
+    kc = 32 or 64 channels per K slice (passed to the kernel as geom[16])."""
     _chk(x, torch.bfloat16, "conv.x")
     _chk(w, torch.bfloat16, "conv.w", 3)
     ref_out = out if out is not None else act_out
@@ -253,8 +254,8 @@ def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=Non
     flat = [int(v) for tp in taps for v in tp]
     ldc = ref_out.stride(-2)
     _call("vcof_conv_igemm", x.data_ptr(), _arr(_ct.c_longlong, [int(v) for v in x_dims]),
-          _arr(_ct.c_longlong, [int(v) for v in x_strides]), w.data_ptr(), w.shape[0] * 32,
-          _arr(_ct.c_short, flat), ntaps, int(tgroup), cin, _arr(_ct.c_int, [int(v) for v in geom]), _p(bias),
+          _arr(_ct.c_longlong, [int(v) for v in x_strides]), w.data_ptr(), w.shape[0] * w.shape[2],
+          _arr(_ct.c_short, flat), ntaps, int(tgroup), cin, _arr(_ct.c_int, [int(v) for v in geom] + [int(w.shape[2])]), _p(bias),
           _p(residual), _p(out), ldc, float(clamp), _p(act_out), _p(act_gamma), _stream(),
           key=f"conv taps={ntaps} cin={cin} n={geom[4]} T={geom[0]} H={geom[1]} W={geom[2]}"
               + ("+act" if act_out is not None else ""))

@@ -18,6 +18,8 @@ are kept (oracle/vae_oracle.py proves the closed form against the reference's ow
 """
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -172,33 +174,50 @@ def _ver(*tensors):
     return tuple((t.data_ptr(), t._version, str(t.device), t.dtype) for t in tensors if t is not None)
 
 
-def _pack_taps(w_taps, bias, cin_p, tgroup=1):
+def _slice_plan(cin, cout, kt=1):
+    """K-slice geometry of one convolution for vcof_conv_igemm: (kc, cin_p, tgroup).
+
+    kc = channels per K slice = one TMA box row (32 -> 64-byte rows, 64 -> 128-byte rows).  Measured on B200
+    (profiles/r1_tma_probe_v2.txt, r1_gpurun17): the kernel's operand feed is bounded by bytes in flight / slot
+    latency, not by the row width, and C = 96 wastes a quarter of a 128-channel K extent, so kc = 32 is the
+    default; VCOF_CONV_KC=64 selects the wide slices (kept correct by tests/test_vae_gpu.py).  Channels are
+    zero-padded to a multiple of kc in the WEIGHTS only (an activation box that reads past C is zero-filled by
+    TMA or multiplied by zero weights).  tgroup = k_t when two ring stages of k_t fused temporal taps fit the
+    kernel's 200 KB operand ring, else 1."""
+    kc = 64 if (os.environ.get("VCOF_CONV_KC") == "64" and cin >= 64) else 32
+    cin_p = (cin + kc - 1) // kc * kc
+    n_tile = _ntile(_pad16(cout))
+    tgroup = kt if 2 * kt * (128 + n_tile) * kc * 2 <= 200 * 1024 else 1
+    return kc, cin_p, tgroup
+
+
+def _pack_taps(w_taps, bias, cin_p, tgroup=1, kc=32):
     """w_taps: fp32 [Cout, Cin, ntaps] (taps ordered group-major, the `tgroup` dt-taps of a group adjacent) ->
-    bf16 [slices, Cout_p16, 32] with slice = ((group * cin_p/32 + chunk) * tgroup + j); bias fp32 [Cout_p16]."""
+    bf16 [slices, Cout_p16, kc] with slice = ((group * cin_p/kc + chunk) * tgroup + j); bias fp32 [Cout_p16]."""
     cout, cin, ntaps = w_taps.shape
     cout_p = _pad16(cout)
     w = torch.zeros((cout_p, ntaps, cin_p), dtype=torch.float32, device=w_taps.device)
     w[:cout, :, :cin] = w_taps.permute(0, 2, 1)
-    w = w.view(cout_p, ntaps // tgroup, tgroup, cin_p // 32, 32).permute(1, 3, 2, 0, 4)   # [G, cc, tg, n, 32]
+    w = w.view(cout_p, ntaps // tgroup, tgroup, cin_p // kc, kc).permute(1, 3, 2, 0, 4)   # [G, cc, tg, n, kc]
     b = torch.zeros(cout_p, dtype=torch.float32, device=w_taps.device)
     if bias is not None:
         b[:cout] = bias.float()
-    return w.reshape(-1, cout_p, 32).to(torch.bfloat16).contiguous(), b
+    return w.reshape(-1, cout_p, kc).to(torch.bfloat16).contiguous(), b
 
 
 def pack_conv(conv):
     """nn.Conv3d [Cout,Cin,kt,kh,kw] / nn.Conv2d [Cout,Cin,kh,kw] -> (packed weight, bias, cin_p, tgroup); taps are
-    ordered (kh, kw)-major with the k_t temporal taps adjacent, so that one TMA box feeds all k_t of them."""
+    ordered (kh, kw)-major with the k_t temporal taps adjacent, so that one TMA box can feed all k_t of them."""
     def build():
         w = conv.weight.detach().float()
         if w.dim() == 4:
             w = w.unsqueeze(2)
         kt = w.shape[2]
         w = w.permute(0, 1, 3, 4, 2).reshape(w.shape[0], w.shape[1], -1)    # taps (i, j, a), a fastest
-        cin_p = _pad32(w.shape[1])
-        pw, pb = _pack_taps(w, conv.bias.detach() if conv.bias is not None else None, cin_p, tgroup=kt)
-        return pw, pb, cin_p, kt
-    return _cached(conv, "plain", _ver(conv.weight, conv.bias), build)
+        kc, cin_p, tg = _slice_plan(w.shape[1], w.shape[0], kt)
+        pw, pb = _pack_taps(w, conv.bias.detach() if conv.bias is not None else None, cin_p, tgroup=tg, kc=kc)
+        return pw, pb, cin_p, tg
+    return _cached(conv, "plain" + os.environ.get("VCOF_CONV_KC", ""), _ver(conv.weight, conv.bias), build)
 
 
 def pack_upsample_conv(conv):
@@ -208,7 +227,7 @@ def pack_upsample_conv(conv):
     taps along each axis collapse onto two source offsets, whose weights are summed (in fp32)."""
     def build():
         w = conv.weight.detach().float()          # [Cout, Cin, 3, 3]
-        cin_p = _pad32(w.shape[1])
+        kc, cin_p, _ = _slice_plan(w.shape[1], w.shape[0])
         packs = {}
         # source offset of kernel index d for output parity p: floor((p + d - 1) / 2)
         for ph in (0, 1):
@@ -226,9 +245,9 @@ def pack_upsample_conv(conv):
                         mats.append(m)
                         taps.append((0, ow, 0, oh, 0))
                 wt = torch.stack(mats, dim=2)                      # [Cout, Cin, 4]
-                packs[(ph, pw_)] = _pack_taps(wt, conv.bias.detach(), cin_p) + (taps,)
+                packs[(ph, pw_)] = _pack_taps(wt, conv.bias.detach(), cin_p, kc=kc) + (taps,)
         return packs, cin_p
-    return _cached(conv, "up", _ver(conv.weight, conv.bias), build)
+    return _cached(conv, "up" + os.environ.get("VCOF_CONV_KC", ""), _ver(conv.weight, conv.bias), build)
 
 
 def _vec(mod, name, t):
@@ -336,8 +355,8 @@ def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None, act_norm=None, 
     returns (raw, act) then (raw is None when want_raw is False)."""
     pw, pb, cin_p, tg = pack_conv(conv)
     T, H, W, C = x.shape
-    if C != cin_p:
-        raise VcofError(f"conv input has {C} channels, packed weight expects {cin_p}")
+    if C != _pad32(conv.weight.shape[1]):
+        raise VcofError(f"conv input has {C} channels, the layer expects {_pad32(conv.weight.shape[1])}")
     k = conv.kernel_size
     kt, kh, kw = (1, k[0], k[1]) if len(k) == 2 else k
     t_shift = 0
