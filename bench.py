@@ -333,6 +333,7 @@ def run_vcof(args):
                 "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
                 "peak_source": f"{peaks['src']} bf16_tflops_sustained", "traffic": None,
                 "flops_per_launch": flops, "avg_launch_ms": ms / n, "launches_timed": n}
+        roof.update(ncu_traffic(attn_key[0]))
     gpu_ms = sum(ms for _, ms in timing.values())
     breakdown = sorted(((k, n, ms) for k, (n, ms) in timing.items()), key=lambda r: -r[2])[:8]
     fl = flops_per_forward(cfg_kw, L)
@@ -357,6 +358,22 @@ def run_vcof(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ncu_traffic(attn_key):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same launch
+    shape (profiles/r1_attn_c2_ncu.json: dram__bytes_read.sum + dram__bytes_write.sum); null for other shapes."""
+    import re
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_attn_c2_ncu.json")
+    m = re.match(r"attn Lq=(\d+) Lk=(\d+) heads=(\d+)", attn_key)
+    if not m or not os.path.exists(path):
+        return {}
+    d = json.load(open(path))
+    sh = d["shape"]
+    if (int(m.group(1)), int(m.group(2)), int(m.group(3))) != (sh["Lq"], sh["Lk"], sh["heads"]):
+        return {}
+    return {"traffic": d["dram_bytes_per_launch"], "traffic_unit": "bytes/launch",
+            "traffic_algorithmic": d["algorithmic_bytes"], "traffic_source": "profiles/r1_attn_c2_ncu.json"}
 
 
 def main():

@@ -70,6 +70,20 @@ int vcof_rmsnorm_rope(void* x, long long ldx, const void* weight, float eps, int
                       int head_dim, const float* rope_table, const int* tpos, int F, int H, int W,
                       int n_t, int n_h, int row_offset, void* stream);
 
+/* Same arithmetic as vcof_rmsnorm_rope, out of place into the column-blocked layout
+ * y[C / cols_per_block][L][cols_per_block] (blocks block_stride elements apart): the send buffer of the
+ * sequence-parallel head exchange (one block of heads per destination rank), so the pack costs no extra pass.
+ * New (the reference's xfuser all-to-all lives in the absent yunchang package, dist/wan_xfuser.py:98). */
+int vcof_rmsnorm_rope_blocked(const void* x, long long ldx, void* y, int cols_per_block, long long block_stride,
+                              const void* weight, float eps, int L, int C, int head_dim, const float* rope_table,
+                              const int* tpos, int F, int H, int W, int n_t, int n_h, int row_offset, void* stream);
+
+/* Copy between a row-major bf16 [rows, C] matrix (pitch ld) and its column-blocked form
+ * [C / cols_per_block][rows][cols_per_block]; to_blocked != 0 packs, 0 unpacks.  Pack / unpack of the head
+ * exchange for tensors that have no normalisation pass (V, and the attention output on the way back). */
+int vcof_copy_blocked(void* rowmajor, long long ld, void* blocked, long long block_stride, long long rows, int C,
+                      int cols_per_block, int to_blocked, void* stream);
+
 /* Patchify latents x_bf16[Cin, F, H, W] -> tokens a_bf16[F*(H/2)*(W/2), Cin*4], column order
  * (c, ph, pw) = the flattened Conv3d weight [C, Cin, 1, 2, 2].  wan_transformer3d.py:870, 879. */
 int vcof_patchify(const void* x, void* a, int Cin, int F, int H, int W, void* stream);

@@ -29,8 +29,18 @@ def _attn(q, k, v, heads, kv_len=None, out=None, **_):
     return o
 
 
+def _copy(rowmajor, blocked, to_blocked):
+    """torch statement of vcof_copy_blocked (include/vcof.h)."""
+    P, rows, cp = blocked.shape
+    if to_blocked:
+        blocked.copy_(rowmajor.view(rows, P, cp).transpose(0, 1))
+        return blocked
+    rowmajor.view(rows, P, cp).copy_(blocked.transpose(0, 1))
+    return rowmajor
+
+
 def _worker(rank, world, port, L, q, mode="gather"):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VCOF_SP_MODE=mode)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from videocof_b200.dist import SequenceParallel
@@ -41,7 +51,7 @@ def _worker(rank, world, port, L, q, mode="gather"):
         full = [torch.randn(seq_len, C) for _ in range(3)]
         for t in full:
             t[L:] = 7.0                                          # padding rows hold junk that must be masked
-        sp = SequenceParallel(attn_fn=_attn)
+        sp = SequenceParallel(attn_fn=_attn, copy_fn=_copy)
         rows = seq_len // world
         sp.configure(kv_len=L, rows=rows)
         ql, kl, vl = (sp.shard(t) for t in full)
@@ -50,7 +60,8 @@ def _worker(rank, world, port, L, q, mode="gather"):
         else:
             assert sp.can_exchange_heads(heads)
             for name, t in (("q", ql), ("k", kl), ("v", vl)):
-                sp.start_exchange(name, t.contiguous())
+                t = t.contiguous()
+                sp.start_exchange(name, sp.pack(t, sp.send_buffer(name, t)))
             out_local = sp.attention_exchanged(heads, out=torch.empty(rows, C))
         gathered = sp.all_gather_rows(out_local)
         ref = _attn(full[0], full[1], full[2], heads, kv_len=L)

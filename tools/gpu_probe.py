@@ -191,6 +191,20 @@ def run_case(c):
         torch.cuda.synchronize()
         stats(got, ref.bfloat16())
         res["ok"] = (not res["nan"]) and res["rel_fro"] < 3e-3
+        # column-blocked output (head-exchange send layout) and the pack / unpack kernel: bit-exact rearrangements
+        for P in (p_ for p_ in (2, 4) if h % p_ == 0):
+            rows = x.shape[0]
+            blk = torch.full((P, rows, C // P), 7.0, dtype=torch.bfloat16, device=dev)
+            x0 = x.clone()
+            ops.rmsnorm_rope_(x0, wgt, 1e-6, d, rope, out_blocked=blk)
+            want = got.view(rows, P, C // P).transpose(0, 1)
+            packed = ops.copy_blocked(got, torch.empty_like(blk), True)
+            back = ops.copy_blocked(torch.empty_like(got), packed, False)
+            torch.cuda.synchronize()
+            exact = bool((blk == want).all()) and bool((x0 == x).all()) and bool((packed == want).all()) \
+                and bool((back == got).all())
+            res[f"blocked_P{P}_exact"] = exact
+            res["ok"] = res["ok"] and exact
     elif kind == "patch":
         F, H, W = c["F"], c["H"], c["W"]
         x = torch.randn(16, F, H, W, device=dev).bfloat16()

@@ -20,6 +20,9 @@ SIGNATURES = {
                          c_int, c_int, c_float, c_void_p],
     "vcof_rmsnorm_rope": [c_void_p, c_ll, c_void_p, c_float, c_int, c_int, c_int, c_void_p,
                           c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "vcof_rmsnorm_rope_blocked": [c_void_p, c_ll, c_void_p, c_int, c_ll, c_void_p, c_float, c_int, c_int, c_int,
+                                  c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "vcof_copy_blocked": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_void_p],
     "vcof_patchify": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vcof_unpatchify": [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vcof_conv_igemm": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,

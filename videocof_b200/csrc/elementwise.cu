@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kRmsThreads)
 rmsnorm_rope_kernel(bf16* __restrict__ x, long long ldx, const bf16* __restrict__ weight, float eps,
                     int C, int head_dim, const float2* __restrict__ table,
                     const int* __restrict__ tpos, int F, int H, int W, int n_t, int n_h,
-                    int row_offset) {
+                    int row_offset, bf16* __restrict__ y, int cols_per_block, long long block_stride) {
   __shared__ float scratch[kRmsThreads / 32];
   const long long row = blockIdx.x;
   uint4* xr = reinterpret_cast<uint4*>(x + row * ldx);
@@ -157,8 +157,34 @@ rmsnorm_rope_kernel(bf16* __restrict__ x, long long ldx, const bf16* __restrict_
         }
         o[e] = pack_bf16x2(yr, yi);
       }
-      xr[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+      const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
+      if (y == nullptr) {
+        xr[idx] = ov;
+      } else {
+        // column-blocked output [C / cols_per_block][rows][cols_per_block]: the send layout of the head exchange
+        const int c = idx * 8;
+        const int blk = c / cols_per_block;
+        *reinterpret_cast<uint4*>(y + blk * block_stride + row * cols_per_block + (c - blk * cols_per_block)) = ov;
+      }
     }
+  }
+}
+
+// Copy between a row-major [rows, C] matrix (pitch ld) and its column-blocked form
+// [C / cols_per_block][rows][cols_per_block] (blocks block_stride elements apart); 16 bytes per thread.
+__global__ void __launch_bounds__(256)
+copy_blocked_kernel(bf16* __restrict__ rowmajor, long long ld, bf16* __restrict__ blocked, long long block_stride,
+                    long long rows, int C, int cols_per_block, int to_blocked) {
+  const int nvec = C >> 3;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / nvec;
+    const int c = int(i - row * nvec) * 8;
+    const int blk = c / cols_per_block;
+    uint4* a = reinterpret_cast<uint4*>(rowmajor + row * ld + c);
+    uint4* b = reinterpret_cast<uint4*>(blocked + blk * block_stride + row * cols_per_block + (c - blk * cols_per_block));
+    if (to_blocked) *b = *a; else *a = *b;
   }
 }
 
@@ -251,10 +277,15 @@ extern "C" int vcof_ln_modulate(const float* x, long long ldx, const float* ln_w
   return 0;
 }
 
-extern "C" int vcof_rmsnorm_rope(void* x, long long ldx, const void* weight, float eps, int L, int C,
-                                 int head_dim, const float* rope_table, const int* tpos, int F,
-                                 int H, int W, int n_t, int n_h, int row_offset, void* stream) {
+static int rmsnorm_rope_launch(void* x, long long ldx, const void* weight, float eps, int L, int C,
+                               int head_dim, const float* rope_table, const int* tpos, int F,
+                               int H, int W, int n_t, int n_h, int row_offset, void* y, int cols_per_block,
+                               long long block_stride, void* stream) {
   VCOF_REQUIRE(L > 0 && C > 0, "vcof_rmsnorm_rope: empty problem");
+  VCOF_REQUIRE(y == nullptr || (cols_per_block > 0 && cols_per_block % 8 == 0 && C % cols_per_block == 0 &&
+                                block_stride >= (long long)L * cols_per_block && block_stride % 8 == 0),
+               "vcof_rmsnorm_rope_blocked: cols_per_block %d must divide C=%d in multiples of 8 and blocks must "
+               "not overlap", cols_per_block, C);
   VCOF_REQUIRE(C % 8 == 0 && C <= kRmsThreads * kRmsMaxVec * 8 && ldx % 8 == 0,
                "vcof_rmsnorm_rope: C=%d / ldx must be multiples of 8, C <= %d", C,
                kRmsThreads * kRmsMaxVec * 8);
@@ -264,7 +295,42 @@ extern "C" int vcof_rmsnorm_rope(void* x, long long ldx, const void* weight, flo
                "vcof_rmsnorm_rope: rope requested without positions");
   rmsnorm_rope_kernel<<<L, kRmsThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<bf16*>(x), ldx, reinterpret_cast<const bf16*>(weight), eps, C, head_dim,
-      reinterpret_cast<const float2*>(rope_table), tpos, F, H, W, n_t, n_h, row_offset);
+      reinterpret_cast<const float2*>(rope_table), tpos, F, H, W, n_t, n_h, row_offset,
+      reinterpret_cast<bf16*>(y), cols_per_block, block_stride);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vcof_rmsnorm_rope(void* x, long long ldx, const void* weight, float eps, int L, int C,
+                                 int head_dim, const float* rope_table, const int* tpos, int F,
+                                 int H, int W, int n_t, int n_h, int row_offset, void* stream) {
+  return rmsnorm_rope_launch(x, ldx, weight, eps, L, C, head_dim, rope_table, tpos, F, H, W, n_t, n_h, row_offset,
+                             nullptr, 0, 0, stream);
+}
+
+extern "C" int vcof_rmsnorm_rope_blocked(const void* x, long long ldx, void* y, int cols_per_block,
+                                         long long block_stride, const void* weight, float eps, int L, int C,
+                                         int head_dim, const float* rope_table, const int* tpos, int F, int H,
+                                         int W, int n_t, int n_h, int row_offset, void* stream) {
+  VCOF_REQUIRE(y != nullptr, "vcof_rmsnorm_rope_blocked: no output");
+  return rmsnorm_rope_launch(const_cast<void*>(x), ldx, weight, eps, L, C, head_dim, rope_table, tpos, F, H, W, n_t,
+                             n_h, row_offset, y, cols_per_block, block_stride, stream);
+}
+
+extern "C" int vcof_copy_blocked(void* rowmajor, long long ld, void* blocked, long long block_stride, long long rows,
+                                 int C, int cols_per_block, int to_blocked, void* stream) {
+  VCOF_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && ld % 8 == 0 && ld >= C, "vcof_copy_blocked: bad shape rows=%lld C=%d",
+               rows, C);
+  VCOF_REQUIRE(cols_per_block > 0 && cols_per_block % 8 == 0 && C % cols_per_block == 0 && block_stride % 8 == 0 &&
+               block_stride >= rows * cols_per_block,
+               "vcof_copy_blocked: cols_per_block %d must divide C=%d in multiples of 8", cols_per_block, C);
+  const long long total = rows * (C >> 3);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  copy_blocked_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<bf16*>(rowmajor), ld, reinterpret_cast<bf16*>(blocked), block_stride, rows, C, cols_per_block,
+      to_blocked);
   VCOF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

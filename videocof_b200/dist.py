@@ -16,7 +16,7 @@ The head output is gathered at the end so every rank runs the identical schedule
 reference's xfuser USP path (videox_fun/dist/wan_xfuser.py:68-111, wan_transformer3d.py:802-816, :949-953,
 :1085-1086), which cannot run VideoCoF's chain-of-frames kwargs.
 
-`attn_fn` is injectable so the sharding / gather logic can be exercised on CPU with gloo
+`attn_fn` / `copy_fn` are injectable so the sharding / exchange logic can be exercised on CPU with gloo
 (tests/test_dist_gloo.py); the product default is the libvcof tcgen05 kernel.
 """
 import os
@@ -26,7 +26,7 @@ import torch.distributed as dist
 
 
 class SequenceParallel:
-    def __init__(self, group=None, attn_fn=None):
+    def __init__(self, group=None, attn_fn=None, copy_fn=None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
         self.group = group if group is not None else dist.group.WORLD
@@ -40,7 +40,11 @@ class SequenceParallel:
         if attn_fn is None:
             from . import ops
             attn_fn = ops.attention
+        if copy_fn is None:
+            from . import ops
+            copy_fn = ops.copy_blocked
         self.attn_fn = attn_fn
+        self.copy_fn = copy_fn        # (rowmajor [rows,C], blocked [P,rows,C/P], to_blocked) pack / unpack kernel
 
     def configure(self, kv_len, rows):
         """kv_len: number of real (non-padding) tokens of the full sequence; rows: tokens per rank."""
@@ -81,9 +85,13 @@ class SequenceParallel:
 
     # -- head exchange (all-to-all) ------------------------------------------------------------------
     def can_exchange_heads(self, heads):
-        """Head exchange needs heads divisible by P (40 heads: P = 2, 4, 8); VCOF_SP_MODE=gather forces the
-        K/V all-gather scheme (A/B measurements)."""
-        return heads % self.world == 0 and os.environ.get("VCOF_SP_MODE", "heads") != "gather"
+        """Head exchange needs heads divisible by P.  Default policy (measured on B200/NVSwitch, profiles/): P >= 4 ->
+        head exchange (at P = 8 the K/V all-gather moves 1.35 GB per layer and rank and leaves ~2 ms exposed);
+        P = 2 -> K/V all-gather (fully hidden behind the V and Q projections).  VCOF_SP_MODE=heads|gather forces."""
+        mode = os.environ.get("VCOF_SP_MODE", "auto")
+        if heads % self.world != 0 or mode == "gather":
+            return False
+        return mode == "heads" or self.world >= 4
 
     def _buf(self, name, shape, like):
         buf = self._xbuf.get(name)
@@ -92,17 +100,23 @@ class SequenceParallel:
             self._xbuf[name] = buf
         return buf
 
-    def start_exchange(self, which, x):
-        """x [rows, C] (this rank's tokens, all heads) -> asynchronously [P*rows, C/P] (all tokens in global order,
-        this rank's heads).  The pack (head-group-major transpose) runs on the compute stream; the all-to-all runs
-        on NCCL's stream and overlaps whatever is launched next."""
-        P = self.world
+    def send_buffer(self, which, x):
+        """Contiguous [P, rows, C/P] send buffer for the [rows, C] projection x: block r holds the heads that rank r
+        will attend over.  The producer writes it directly (ops.rmsnorm_rope_(..., out_blocked=) for Q and K,
+        `pack` for V), so the exchange needs no separate transpose pass."""
         rows, C = x.shape
-        cp = C // P
-        send = self._buf("s" + which, (P, rows, cp), x)
-        send.copy_(x.view(rows, P, cp).transpose(0, 1))
-        recv = self._buf("r" + which, (P * rows, cp), x)
-        work = dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group, async_op=True)
+        return self._buf("s" + which, (self.world, rows, C // self.world), x)
+
+    def pack(self, x, blocked):
+        return self.copy_fn(x, blocked, True)
+
+    def start_exchange(self, which, blocked):
+        """blocked [P, rows, C/P] (this rank's tokens, heads grouped by destination) -> asynchronously
+        [P*rows, C/P] (all tokens in global order, this rank's heads).  The all-to-all runs on NCCL's stream and
+        overlaps whatever is launched next."""
+        P, rows, cp = blocked.shape
+        recv = self._buf("r" + which, (P * rows, cp), blocked)
+        work = dist.all_to_all_single(recv.view(-1), blocked.view(-1), group=self.group, async_op=True)
         self._pending[which] = (recv, work)
 
     def attention_exchanged(self, heads, out):
@@ -118,7 +132,7 @@ class SequenceParallel:
         rows, cp = q.shape[0] // P, q.shape[1]
         back = self._buf("b", (P, rows, cp), q)
         dist.all_to_all_single(back.view(-1), o.view(-1), group=self.group)      # chunk r of o = rank r's tokens
-        out.view(rows, P, cp).copy_(back.transpose(0, 1))
+        self.copy_fn(out, back, False)
         return out
 
     def all_gather_rows(self, y):

@@ -128,15 +128,16 @@ class WanAttentionBlock(nn.Module):
             ops.rmsnorm_rope_(ws.k, sa.norm_k.weight, sa.eps, hd, rope)
             ops.attention(ws.q, ws.k, ws.v, n, kv_len=kv_len, out=ws.a)
         elif sp.can_exchange_heads(n):
-            # head exchange: each projection's all-to-all overlaps the next projection (dist.py)
-            ops.gemm(ws.a, sa.q.weight, sa.q.bias, "bias", out=ws.q)
-            ops.rmsnorm_rope_(ws.q, sa.norm_q.weight, sa.eps, hd, rope)
-            sp.start_exchange("q", ws.q)
-            ops.gemm(ws.a, sa.k.weight, sa.k.bias, "bias", out=ws.k)
-            ops.rmsnorm_rope_(ws.k, sa.norm_k.weight, sa.eps, hd, rope)
-            sp.start_exchange("k", ws.k)
+            # head exchange (dist.py): every projection lands in its all-to-all send layout — V through a pack
+            # kernel, Q and K straight from the norm/RoPE kernel — and its exchange overlaps the next projection
             ops.gemm(ws.a, sa.v.weight, sa.v.bias, "bias", out=ws.v)
-            sp.start_exchange("v", ws.v)
+            sp.start_exchange("v", sp.pack(ws.v, sp.send_buffer("v", ws.v)))
+            ops.gemm(ws.a, sa.q.weight, sa.q.bias, "bias", out=ws.q)
+            sp.start_exchange("q", ops.rmsnorm_rope_(ws.q, sa.norm_q.weight, sa.eps, hd, rope,
+                                                     out_blocked=sp.send_buffer("q", ws.q)))
+            ops.gemm(ws.a, sa.k.weight, sa.k.bias, "bias", out=ws.k)
+            sp.start_exchange("k", ops.rmsnorm_rope_(ws.k, sa.norm_k.weight, sa.eps, hd, rope,
+                                                     out_blocked=sp.send_buffer("k", ws.k)))
             sp.attention_exchanged(n, out=ws.a)
         else:
             # K first so that its NVLink all-gather overlaps the V and Q projections, then V overlaps Q

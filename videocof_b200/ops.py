@@ -171,11 +171,28 @@ class RopeSpec:
         self.F, self.H, self.W, self.n_t, self.n_h, self.row_offset = F, H, W, n_t, n_h, row_offset
 
 
-def rmsnorm_rope_(x, weight, eps, head_dim, rope=None):
-    """In place: WanRMSNorm over the full row, then (optionally) RoPE.  x bf16 [L,C]."""
+def _chk_blocked(blocked, rows, C, what):
+    _chk(blocked, torch.bfloat16, what, 3)
+    nb, r, cp = blocked.shape
+    if r != rows or nb * cp != C or not blocked.is_contiguous():
+        raise _lib.VcofError(f"{what}: blocked buffer {tuple(blocked.shape)} does not tile [{rows}, {C}]")
+    return cp, blocked.stride(0)
+
+
+def rmsnorm_rope_(x, weight, eps, head_dim, rope=None, out_blocked=None):
+    """WanRMSNorm over the full row, then (optionally) RoPE.  x bf16 [L,C]; in place, or — with
+    out_blocked = a contiguous [P, L, C/P] buffer — out of place into that column-blocked layout (x untouched)."""
     _chk(x, torch.bfloat16, "rmsnorm_rope.x", 2)
     _chk(weight, torch.bfloat16, "rmsnorm_rope.weight", 1)
     L, C = x.shape
+    if out_blocked is not None:
+        cp, bs = _chk_blocked(out_blocked, L, C, "rmsnorm_rope.out_blocked")
+        r = rope
+        _call("vcof_rmsnorm_rope_blocked", x.data_ptr(), x.stride(0), out_blocked.data_ptr(), cp, bs,
+              weight.data_ptr(), float(eps), L, C, head_dim, _p(None if r is None else r.table),
+              _p(None if r is None else r.tpos), *((1, 1, 1, 0, 0, 0) if r is None else
+                                                   (r.F, r.H, r.W, r.n_t, r.n_h, r.row_offset)), _stream())
+        return out_blocked
     if rope is None:
         _call("vcof_rmsnorm_rope", x.data_ptr(), x.stride(0), weight.data_ptr(), float(eps), L, C,
               head_dim, None, None, 1, 1, 1, 0, 0, 0, _stream())
@@ -186,6 +203,16 @@ def rmsnorm_rope_(x, weight, eps, head_dim, rope=None):
               head_dim, rope.table.data_ptr(), rope.tpos.data_ptr(), rope.F, rope.H, rope.W,
               rope.n_t, rope.n_h, rope.row_offset, _stream())
     return x
+
+
+def copy_blocked(rowmajor, blocked, to_blocked):
+    """Pack (to_blocked) a row-major bf16 [rows, C] matrix into a contiguous [P, rows, C/P] buffer, or unpack."""
+    _chk(rowmajor, torch.bfloat16, "copy_blocked.rowmajor", 2)
+    rows, C = rowmajor.shape
+    cp, bs = _chk_blocked(blocked, rows, C, "copy_blocked.blocked")
+    _call("vcof_copy_blocked", rowmajor.data_ptr(), rowmajor.stride(0), blocked.data_ptr(), bs, rows, C, cp,
+          1 if to_blocked else 0, _stream())
+    return blocked if to_blocked else rowmajor
 
 
 def patchify(x):
