@@ -34,6 +34,8 @@ int vcof_abi_version(void);
 #define VCOF_EPI_BIAS_GATE_RES_F32 2 /* out_f32 += gate[n] * bf16(acc + bias)  (gate NULL=1) */
 #define VCOF_EPI_BIAS_F32 3          /* out_f32  = float(bf16(acc + bias))                   */
 #define VCOF_EPI_RAW_F32 4           /* out_f32  = acc + bias (unrounded; attention scores)   */
+#define VCOF_EPI_GATE_ACCUM_BF16 5   /* out_bf16 = bf16(float(out_bf16) + gate[n] * acc): in-place LoRA merge
+                                        W += multiplier * alpha/rank * up @ down (utils/lora_utils.py:482-496) */
 
 /* D[M,N] = A[M,K] (bf16) x W[N,K]^T (bf16, nn.Linear layout) with fused epilogue; tcgen05 +
  * TMEM + TMA.  Replaces nn.Linear q/k/v/o, ffn.0/ffn.2, text_embedding, head.head and the

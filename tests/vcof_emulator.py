@@ -10,6 +10,9 @@ def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
     acc = a.float() @ w.float().t()
     if bias is not None:
         acc = acc + bias.float()
+    if epilogue == "gate_accum":          # in place: out = bf16(float(out) + gate[n] * acc)
+        out.copy_((out.float() + gate.float() * acc).to(torch.bfloat16))
+        return out
     if epilogue == "raw_f32":
         res = acc
     elif epilogue == "bias":

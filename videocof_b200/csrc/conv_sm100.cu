@@ -16,12 +16,14 @@
 //   stride-2 down-sampling Conv2d (5-D "parity" view of the input), the nearest-2x + Conv2d up-sampler
 //   (four parity sub-convolutions with folded 2x2 taps; the 4x tensor is never materialised), and the
 //   (3,1,1) temporal convs of up/down-sampling (:107-163) incl. the frame interleave on store.
+#include <cstdlib>
+#include <type_traits>
 #include "vcof_common.cuh"
 #include "../../include/vcof.h"
 
 namespace vcof {
 
-constexpr int kCvThreads = 192;
+constexpr int kCvThreads = 256;               // warps 0-3 epilogue, 4 TMA (A), 5 MMA, 6 TMA (B), 7 idle
 constexpr int kCvMaxStages = 16;             // ring depth is chosen at launch: smem / (A + B bytes of this conv)
 constexpr int kCvRows = 128;                 // positions per tile (= TMEM lanes)
 constexpr int kCvData = 200 * 1024;          // operand ring budget
@@ -58,6 +60,8 @@ struct ConvArgs {
   int interleave_half;        // > 0: channels >= this go to frame+1 and are stored at (n - half)
   int n_store;                // channels actually stored per position (<= n_total)
   int stages, stage_bytes;    // TMA ring geometry chosen at launch
+  int producers;              // 2: activation and weight boxes are issued by lanes of different warps (one lane
+                              // sustains ~1 barrier round trip per ~520 clk, profiles/r1_tma_probe_v2.txt); 1: one lane
   int tgroup;                 // consecutive taps that differ only in dt (3 for k_t = 3, else 1): ONE 5-D box with
                               // t-extent tgroup and ONE rank-3 weight box feed tgroup taps — the TMA unit's cost
                               // is per box (profiles/r1_tma_probe.txt), so boxes must be as large as possible
@@ -99,7 +103,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 5) {
     if (lane == 0) {
       for (int i = 0; i < kCvMaxStages; ++i) {
-        mbar_init(bar_full + 8 * i, 1);
+        mbar_init(bar_full + 8 * i, p.producers);
         mbar_init(bar_empty + 8 * i, 1);
       }
       for (int i = 0; i < 2; ++i) {
@@ -138,8 +142,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     n0 = nt * p.n_tile;
   };
 
-  if (warp == 4) {
+  if (warp == 4 || (warp == 6 && p.producers == 2)) {
     if (lane == 0) {
+      const bool load_a = warp == 4;
+      const bool load_b = (warp == 6) || (p.producers == 1);
+      const uint32_t tx = p.tgroup * ((load_a ? a_bytes : 0) + (load_b ? b_bytes : 0));
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -149,15 +156,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const ConvTap tp = p.taps[g * p.tgroup];            // first tap of the group (lowest dt)
           for (int cc = 0; cc < p.cin_chunks; ++cc) {
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            mbar_expect_tx(bar_full + 8 * s, p.tgroup * (a_bytes + b_bytes));
+            mbar_expect_tx(bar_full + 8 * s, tx);
             uint8_t* st = smem + s * kCvStage;
             // [kc c, 16 w, 1, 8 h, tgroup t] -> tgroup consecutive 128-row K-major tiles
-            tma_load_5d(smem_u32(st), &tmX, bar_full + 8 * s, tp.c_base + cc * p.kc, w0 + tp.dw, tp.p, h0 + tp.dh,
-                        t * p.t_stride + tp.dt);
-            const int slice = (g * p.cin_chunks + cc) * p.tgroup;
-            for (int j = 0; j < nsub; ++j)
-              tma_load_3d(smem_u32(st + p.tgroup * a_bytes + j * p.tgroup * n_sub * row_bytes), &tmW, bar_full + 8 * s, 0,
-                          n0 + j * n_sub, slice);
+            if (load_a)
+              tma_load_5d(smem_u32(st), &tmX, bar_full + 8 * s, tp.c_base + cc * p.kc, w0 + tp.dw, tp.p, h0 + tp.dh,
+                          t * p.t_stride + tp.dt);
+            if (load_b) {
+              const int slice = (g * p.cin_chunks + cc) * p.tgroup;
+              for (int j = 0; j < nsub; ++j)
+                tma_load_3d(smem_u32(st + p.tgroup * a_bytes + j * p.tgroup * n_sub * row_bytes), &tmW,
+                            bar_full + 8 * s, 0, n0 + j * n_sub, slice);
+            }
             if (++s == kCvStages) { s = 0; ph ^= 1; }
           }
         }
@@ -165,9 +175,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   } else if (warp == 5) {
     if (lane == 0) {
+      // Single-lane code is latency-bound (one dependent ALU op ~ 5 clk) and sits on the ring's slot cycle, so the
+      // issue loop is descriptor += constant only: all smem addresses are < 256 KB and 16-byte multiples, hence an
+      // offset is a plain add on the descriptor's 14-bit address field.
       const uint32_t idesc = make_idesc_bf16(128, n_sub, false, false);
       const bool wide = p.kc == 64;
-      const int ksteps = p.kc / 16;
+      const uint64_t dflags = wide ? (kDescVersion1 | kDescSwizzle128 | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 16))
+                                   : (kDescVersion1 | kDescSwizzle64 | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 16));
+      const uint64_t desc0 = dflags | uint64_t((smem_u32(smem) & 0x3FFFF) >> 4);
+      const uint32_t stage_step = kCvStage >> 4;
+      const uint32_t a_step = a_bytes >> 4;                         // next temporal tap of the A box
+      const uint32_t b_off = (p.tgroup * a_bytes) >> 4;             // B tiles follow the tgroup A tiles
+      const uint32_t b_step = (n_sub * row_bytes) >> 4;             // next temporal tap of a B sub-tile
+      const int tg = p.tgroup;
+      auto issue_stage = [&](auto ks_tag, uint64_t a_desc, uint32_t d_tmem, bool first) {
+        constexpr int kSteps = decltype(ks_tag)::value;
+        uint64_t b_desc = a_desc + b_off;
+        for (int dt = 0; dt < tg; ++dt) {
+#pragma unroll
+          for (int ks = 0; ks < kSteps; ++ks) {
+            umma_ss(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, !(first && dt == 0 && ks == 0));
+            if (nsub == 2)
+              umma_ss(d_tmem + n_sub, a_desc + ks * 2, b_desc + tg * b_step + ks * 2, idesc,
+                      !(first && dt == 0 && ks == 0));
+          }
+          a_desc += a_step;
+          b_desc += b_step;
+        }
+      };
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -180,27 +215,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int k = 0; k < num_k; ++k) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const uint32_t a_stage = smem_u32(smem + s * kCvStage);
-          const uint32_t b_stage = a_stage + p.tgroup * a_bytes;
-          for (int dt = 0; dt < p.tgroup; ++dt) {
-            const uint32_t a_base = a_stage + dt * a_bytes;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              for (int j = 0; j < nsub; ++j) {
-                const uint32_t a_addr = a_base + ks * 32;
-                const uint32_t b_addr = b_stage + (j * p.tgroup + dt) * n_sub * row_bytes + ks * 32;
-                umma_ss(d_tmem + j * n_sub, wide ? make_desc_kmajor_sw128(a_addr) : make_desc_kmajor_sw64(a_addr),
-                        wide ? make_desc_kmajor_sw128(b_addr) : make_desc_kmajor_sw64(b_addr), idesc,
-                        (k | dt | ks) != 0);
-              }
-            }
-          }
+          const uint64_t a_desc = desc0 + uint32_t(s) * stage_step;
+          if (wide) issue_stage(std::integral_constant<int, 4>{}, a_desc, d_tmem, k == 0);
+          else issue_stage(std::integral_constant<int, 2>{}, a_desc, d_tmem, k == 0);
           umma_commit(bar_empty + 8 * s);
           if (++s == kCvStages) { s = 0; ph ^= 1; }
         }
         umma_commit(bar_tfull + 8 * acc);
       }
     }
-  } else {
+  } else if (warp < 4) {
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int t, h0, w0, n0;
@@ -536,6 +560,13 @@ extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const lon
                    "vcof_conv_igemm: taps of group %d must differ only by consecutive dt", g);
     }
   a.tgroup = tgroup;
+  {
+    static const int producers = [] {
+      const char* e = getenv("VCOF_CONV_PRODUCERS");
+      return (e != nullptr && e[0] == '1') ? 1 : 2;
+    }();
+    a.producers = producers;
+  }
   a.stage_bytes = tgroup * (kCvRows + a.n_tile) * kc * 2;    // multiples of 1 KB keep the swizzled tiles aligned
   a.stages = kCvData / a.stage_bytes;
   VCOF_REQUIRE(a.stages >= 2, "vcof_conv_igemm: stage of %d bytes leaves no ring", a.stage_bytes);

@@ -14,6 +14,7 @@
 // (reference videox_fun/models/wan_transformer3d.py:264-267, 457-459, 543) and fuses
 // what the reference runs as separate ATen kernels afterwards: bias, GELU(tanh)
 // (:458), the AdaLN gate and fp32 residual accumulate (:499, :504, :511).
+#include <cstdlib>
 #include "vcof_common.cuh"
 #include "../../include/vcof.h"
 
@@ -21,7 +22,7 @@ namespace vcof {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 256;   // warps 0-3 epilogue, 4 TMA (A, or A+B), 5 MMA, 6 TMA (B) when two producer lanes, 7 idle
 
 struct GemmArgs {
   int M, N, K;
@@ -30,6 +31,8 @@ struct GemmArgs {
   void* out;          // bf16 or fp32 [M, ldo]
   long long ldo;
   int group_m;
+  int producers;      // 1: one lane issues both operand boxes per stage; 2: A and B boxes come from lanes of different
+                      // warps (one lane sustains ~1 barrier round trip per ~520 clk, profiles/r1_tma_probe_v2.txt)
 };
 
 template <int BN>
@@ -83,7 +86,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 5) {
     if (lane == 0) {
       for (int i = 0; i < S; ++i) {
-        mbar_init(bar_full + 8 * i, 1);
+        mbar_init(bar_full + 8 * i, p.producers);
         mbar_init(bar_empty + 8 * i, 1);
       }
       for (int i = 0; i < 2; ++i) {
@@ -105,9 +108,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + kBK - 1) / kBK;
 
-  if (warp == 4) {
-    // ---------------- TMA producer ----------------
+  if (warp == 4 || (warp == 6 && p.producers == 2)) {
+    // ---------------- TMA producer(s) ----------------
     if (lane == 0) {
+      const bool load_a = warp == 4;
+      const bool load_b = (warp == 6) || (p.producers == 1);
+      const uint32_t tx = (load_a ? Cfg::kABytes : 0) + (load_b ? Cfg::kBBytes : 0);
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -115,11 +121,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          mbar_expect_tx(bar_full + 8 * s, Cfg::kStageBytes);
-          tma_load_2d(smem_u32(sA + s * Cfg::kABytes), &tmA, bar_full + 8 * s, kb * kBK,
-                      m_blk * kBM);
-          tma_load_2d(smem_u32(sB + s * Cfg::kBBytes), &tmB, bar_full + 8 * s, kb * kBK,
-                      n_blk * BN);
+          mbar_expect_tx(bar_full + 8 * s, tx);
+          if (load_a)
+            tma_load_2d(smem_u32(sA + s * Cfg::kABytes), &tmA, bar_full + 8 * s, kb * kBK, m_blk * kBM);
+          if (load_b)
+            tma_load_2d(smem_u32(sB + s * Cfg::kBBytes), &tmB, bar_full + 8 * s, kb * kBK, n_blk * BN);
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
@@ -153,7 +159,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         umma_commit(bar_tfull + 8 * acc);
       }
     }
-  } else {
+  } else if (warp < 4) {
     // ---------------- epilogue warps 0..3 ----------------
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -248,6 +254,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 o[j] += g * bf16_round(v[j]);
               }
           }
+        } else if (EPI == VCOF_EPI_GATE_ACCUM_BF16) {
+          // W[row, n] = bf16(float(W[row, n]) + gate[n] * acc): in-place LoRA merge (lora_utils.py:496: the weight is
+          // lifted to fp32, updated and cast back)
+          bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + n0;
+          if (full_chunk) {
+            uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 w = o4[q];
+              const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+              const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gate + n0) + q * 2);
+              const float4 gb = __ldg(reinterpret_cast<const float4*>(p.gate + n0) + q * 2 + 1);
+              const float2 f0 = __bfloat1622float2(w2[0]), f1 = __bfloat1622float2(w2[1]);
+              const float2 f2 = __bfloat1622float2(w2[2]), f3 = __bfloat1622float2(w2[3]);
+              uint4 r;
+              r.x = pack_bf16x2(f0.x + ga.x * v[q * 8 + 0], f0.y + ga.y * v[q * 8 + 1]);
+              r.y = pack_bf16x2(f1.x + ga.z * v[q * 8 + 2], f1.y + ga.w * v[q * 8 + 3]);
+              r.z = pack_bf16x2(f2.x + gb.x * v[q * 8 + 4], f2.y + gb.y * v[q * 8 + 5]);
+              r.w = pack_bf16x2(f3.x + gb.z * v[q * 8 + 6], f3.y + gb.w * v[q * 8 + 7]);
+              o4[q] = r;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) o[j] = __float2bfloat16_rn(__bfloat162float(o[j]) + p.gate[n0 + j] * v[j]);
+          }
         } else if (EPI == VCOF_EPI_RAW_F32) {  // out = acc + bias, unrounded (attention scores)
           float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0;
           if (full_chunk) {
@@ -320,6 +352,8 @@ static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
       return launch_gemm<BN, VCOF_EPI_BIAS_GATE_RES_F32>(tmA, tmB, args, stream);
     case VCOF_EPI_BIAS_F32: return launch_gemm<BN, VCOF_EPI_BIAS_F32>(tmA, tmB, args, stream);
     case VCOF_EPI_RAW_F32: return launch_gemm<BN, VCOF_EPI_RAW_F32>(tmA, tmB, args, stream);
+    case VCOF_EPI_GATE_ACCUM_BF16:
+      return launch_gemm<BN, VCOF_EPI_GATE_ACCUM_BF16>(tmA, tmB, args, stream);
   }
   set_last_error("vcof_gemm_bf16: unknown epilogue %d", epi);
   return -1;
@@ -344,6 +378,8 @@ extern "C" int vcof_gemm_bf16(const void* a, long long lda, const void* w, long 
                "vcof_gemm_bf16: bias not 16B aligned");
   VCOF_REQUIRE(gate == nullptr || (reinterpret_cast<uintptr_t>(gate) & 15) == 0,
                "vcof_gemm_bf16: gate not 16B aligned");
+  VCOF_REQUIRE(epilogue != VCOF_EPI_GATE_ACCUM_BF16 || (gate != nullptr && bias == nullptr),
+               "vcof_gemm_bf16: the accumulate epilogue needs a gate vector and takes no bias");
   const int BN = (N > 128) ? 256 : (N > 64 ? 128 : 64);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d_bf16(&tmA, a, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kBM);
@@ -357,6 +393,13 @@ extern "C" int vcof_gemm_bf16(const void* a, long long lda, const void* w, long 
   args.out = out;
   args.ldo = ldo;
   args.group_m = 8;
+  {
+    static const int producers = [] {
+      const char* e = getenv("VCOF_GEMM_PRODUCERS");
+      return (e != nullptr && e[0] == '1') ? 1 : 2;
+    }();
+    args.producers = producers;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (BN == 256) return dispatch_epi<256>(epilogue, tmA, tmB, args, st);
   if (BN == 128) return dispatch_epi<128>(epilogue, tmA, tmB, args, st);

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-EPI = {"bias": 0, "bias_gelu": 1, "bias_gate_res": 2, "bias_f32": 3, "raw_f32": 4}
+EPI = {"bias": 0, "bias_gelu": 1, "bias_gate_res": 2, "bias_f32": 3, "raw_f32": 4, "gate_accum": 5}
 
 # kernel launches since the last reset (bench.py reports it as gpu_launches)
 _launches = 0
@@ -86,7 +86,8 @@ def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
     """out = epilogue(a @ w.T + bias).  a [M,K] bf16, w [N,K] bf16 (nn.Linear layout).
 
     epilogue: "bias" -> bf16 [M,N]; "bias_gelu" -> bf16 gelu_tanh; "bias_f32" -> fp32 (value
-    rounded through bf16); "bias_gate_res" -> `out` (fp32 [M,N], required) += gate * bf16(.)
+    rounded through bf16); "bias_gate_res" -> `out` (fp32 [M,N], required) += gate * bf16(.);
+    "gate_accum" -> `out` (bf16 [M,N], required) = bf16(float(out) + gate[n] * (a @ w.T)) (LoRA merge)
     """
     _chk(a, torch.bfloat16, "gemm.a", 2)
     _chk(w, torch.bfloat16, "gemm.w", 2)
@@ -107,6 +108,10 @@ def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
         if out is None:
             out = torch.empty((M, N), dtype=torch.float32, device=a.device)
         _chk(out, torch.float32, "gemm.out", 2)
+    elif epi == 5:
+        if out is None or gate is None or bias is not None:
+            raise _lib.VcofError("gemm: gate_accum updates `out` in place with a per-column gate and no bias")
+        _chk(out, torch.bfloat16, "gemm.out", 2)
     else:
         if out is None:
             out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
