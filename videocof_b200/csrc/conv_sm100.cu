@@ -147,6 +147,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const bool load_a = warp == 4;
       const bool load_b = (warp == 6) || (p.producers == 1);
       const uint32_t tx = p.tgroup * ((load_a ? a_bytes : 0) + (load_b ? b_bytes : 0));
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t b_off_bytes = p.tgroup * a_bytes;
+      const uint32_t b_sub_bytes = p.tgroup * n_sub * row_bytes;
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -154,19 +157,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         decode(tile, t, h0, w0, n0);
         for (int g = 0; g < ngroups; ++g) {
           const ConvTap tp = p.taps[g * p.tgroup];            // first tap of the group (lowest dt)
+          // everything the issue needs is computed BEFORE the wait: the instructions between a barrier wake-up and the
+          // TMA issue sit on the ring's slot cycle (single-lane code, ~5 clk per dependent op)
+          const int cw = w0 + tp.dw, chh = h0 + tp.dh, ct = t * p.t_stride + tp.dt;
           for (int cc = 0; cc < p.cin_chunks; ++cc) {
+            const uint32_t st = smem_base + s * kCvStage;
+            const uint32_t bar = bar_full + 8 * s;
+            const int cch = tp.c_base + cc * p.kc;
+            const int slice = (g * p.cin_chunks + cc) * p.tgroup;
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            mbar_expect_tx(bar_full + 8 * s, tx);
-            uint8_t* st = smem + s * kCvStage;
+            mbar_expect_tx(bar, tx);
             // [kc c, 16 w, 1, 8 h, tgroup t] -> tgroup consecutive 128-row K-major tiles
-            if (load_a)
-              tma_load_5d(smem_u32(st), &tmX, bar_full + 8 * s, tp.c_base + cc * p.kc, w0 + tp.dw, tp.p, h0 + tp.dh,
-                          t * p.t_stride + tp.dt);
+            if (load_a) tma_load_5d(st, &tmX, bar, cch, cw, tp.p, chh, ct);
             if (load_b) {
-              const int slice = (g * p.cin_chunks + cc) * p.tgroup;
-              for (int j = 0; j < nsub; ++j)
-                tma_load_3d(smem_u32(st + p.tgroup * a_bytes + j * p.tgroup * n_sub * row_bytes), &tmW,
-                            bar_full + 8 * s, 0, n0 + j * n_sub, slice);
+              tma_load_3d(st + b_off_bytes, &tmW, bar, 0, n0, slice);
+              if (nsub == 2) tma_load_3d(st + b_off_bytes + b_sub_bytes, &tmW, bar, 0, n0 + n_sub, slice);
             }
             if (++s == kCvStages) { s = 0; ph ^= 1; }
           }
@@ -213,9 +218,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int k = 0; k < num_k; ++k) {
+          const uint64_t a_desc = desc0 + uint32_t(s) * stage_step;
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const uint64_t a_desc = desc0 + uint32_t(s) * stage_step;
           if (wide) issue_stage(std::integral_constant<int, 4>{}, a_desc, d_tmem, k == 0);
           else issue_stage(std::integral_constant<int, 2>{}, a_desc, d_tmem, k == 0);
           umma_commit(bar_empty + 8 * s);

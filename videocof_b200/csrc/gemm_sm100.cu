@@ -144,14 +144,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          // descriptors before the wait: single-lane instructions after the wake-up sit on the ring's slot cycle
+          const uint64_t a_desc = make_desc_kmajor_sw128(smem_u32(sA + s * Cfg::kABytes));
+          const uint64_t b_desc = make_desc_kmajor_sw128(smem_u32(sB + s * Cfg::kBBytes));
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + s * Cfg::kABytes);
-          const uint32_t b_base = smem_u32(sB + s * Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
-            umma_ss(d_tmem, make_desc_kmajor_sw128(a_base + k * 32),
-                    make_desc_kmajor_sw128(b_base + k * 32), idesc, (kb | k) != 0);
+            // +32 bytes per K=16 step = +2 in the descriptor's 16-byte address field
+            umma_ss(d_tmem, a_desc + k * 2, b_desc + k * 2, idesc, (kb | k) != 0);
           }
           umma_commit(bar_empty + 8 * s);
           if (++s == S) { s = 0; ph ^= 1; }
