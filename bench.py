@@ -281,7 +281,8 @@ def run_vcof(args):
 
     # ---- whole pipeline through WanPipeline.__call__ (VAE encode -> 4 steps -> VAE decode x2), host in/out
     pipe_stats = None
-    if not args.no_pipeline and args.workload != "c5":
+    # (default at N = 1; at N > 1 only with --pipeline: the scaling runs measure the step metric)
+    if not args.no_pipeline and args.workload != "c5" and (world == 1 or args.pipeline):
         from videocof_b200.pipeline import WanPipeline
         from videocof_b200.vae import AutoencoderKLWan
         torch.manual_seed(2)
@@ -387,6 +388,8 @@ def main():
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed steps (use with ncu --profile-from-start off)")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the WanPipeline (VAE + 4 steps) end-to-end leg")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="also run the WanPipeline leg at N > 1 (DiT sequence-parallel, VAE frame-sharded)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
