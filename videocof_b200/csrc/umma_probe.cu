@@ -7,6 +7,10 @@
 //   D[128,128] (fp32) = A[128,64] (bf16) * B[128,64]^T (bf16)
 //   mode bit0: B operand staged MN-major (as the attention V tile) instead of K-major
 //   mode bit1: A operand fed from TMEM (as the attention P tile) instead of smem
+//   mode bits 4-6: A is a [136, 64] matrix staged with the swizzle of its ABSOLUTE smem rows and the MMA reads the
+//             128-row window starting `shift` rows in (a row-shifted view of a resident tile, as an im2col-free
+//             convolution would take one per filter tap); bit 7: put (start_address >> 7) & 7 into the descriptor's
+//             base-offset field (bits 49-51)
 #include "vcof_common.cuh"
 #include "../../include/vcof.h"
 
@@ -15,15 +19,18 @@ namespace vcof {
 __global__ void __launch_bounds__(128, 1)
 umma_probe_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, float* __restrict__ d,
                   int mode) {
-  __shared__ __align__(1024) uint8_t sA[128 * 128];   // 128 rows x 64 bf16
+  __shared__ __align__(1024) uint8_t sA[136 * 128];   // 128 (+8 for the shifted-view mode) rows x 64 bf16
   __shared__ __align__(1024) uint8_t sB[128 * 128];   // K-major: 128 n-rows x 64 k | MN-major: 2 x [64 k-rows x 64 n]
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const bool b_mn = mode & 1, a_tmem = mode & 2;
+  const int shift = (mode >> 4) & 7;
+  const bool use_bo = mode & 128;
+  const int a_rows = shift ? 136 : 128;
   const int tid = threadIdx.x, warp = tid >> 5;
 
   // ---- stage operands (swizzle: 16-byte chunk index ^= row & 7) ----
-  for (int i = tid; i < 128 * 64; i += 128) {
+  for (int i = tid; i < a_rows * 64; i += 128) {
     const int r = i / 64, c = i % 64;
     const int off = r * 128 + (((c >> 3) ^ (r & 7)) << 4) + (c & 7) * 2;
     *reinterpret_cast<bf16*>(sA + off) = a[r * 64 + c];
@@ -74,7 +81,12 @@ umma_probe_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, float*
       if (a_tmem)
         umma_ts(tD, tA + k * 8, bd, idesc, k != 0);
       else
-        umma_ss(tD, make_desc_kmajor_sw128(smem_u32(sA) + k * 32), bd, idesc, k != 0);
+      {
+        const uint32_t a_start = smem_u32(sA) + shift * 128;
+        uint64_t ad = make_desc_kmajor_sw128(a_start + k * 32);
+        if (use_bo) ad |= uint64_t((a_start >> 7) & 7) << 49;
+        umma_ss(tD, ad, bd, idesc, k != 0);
+      }
     }
     umma_commit(smem_u32(&bar));
   }
