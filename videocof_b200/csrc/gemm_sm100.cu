@@ -57,6 +57,147 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
   n_blk = r / gsz;
 }
 
+// One accumulator tile (this thread's row of 128 lanes x BN columns at t_row) -> epilogue -> global memory.
+template <int BN, int EPI>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_row, int row, int n_blk) {
+  const bool row_ok = row < p.M;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int n0 = n_blk * BN + c * 32;
+      if (n0 >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(t_row + c * 32, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      const bool full_chunk = (n0 + 32 <= p.N);
+      if (p.bias != nullptr) {
+        if (full_chunk) {
+          const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 b = __ldg(bp + q);
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __bfloat1622float2(b2[e]);
+              v[q * 8 + e * 2] += f.x;
+              v[q * 8 + e * 2 + 1] += f.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) v[j] += __bfloat162float(p.bias[n0 + j]);
+        }
+      }
+      if (EPI == VCOF_EPI_BIAS_GELU_BF16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(bf16_round(v[j]));
+      }
+      if (!row_ok) continue;
+      if (EPI == VCOF_EPI_BIAS_BF16 || EPI == VCOF_EPI_BIAS_GELU_BF16) {
+        bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + n0;
+        if (full_chunk) {
+          uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 w;
+            w.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            o4[q] = w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
+        }
+      } else if (EPI == VCOF_EPI_BIAS_GATE_RES_F32) {
+        // x[row, n] += gate[n] * bf16(acc + bias)   (reference :499 / :504 / :511:
+        // the Linear output is a bf16 tensor, the residual stream is fp32)
+        float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0;
+        if (full_chunk) {
+          float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 x = o4[q];
+            float g0 = 1.f, g1 = 1.f, g2 = 1.f, g3 = 1.f;
+            if (p.gate != nullptr) {
+              float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + n0) + q);
+              g0 = g.x; g1 = g.y; g2 = g.z; g3 = g.w;
+            }
+            x.x += g0 * bf16_round(v[q * 4 + 0]);
+            x.y += g1 * bf16_round(v[q * 4 + 1]);
+            x.z += g2 * bf16_round(v[q * 4 + 2]);
+            x.w += g3 * bf16_round(v[q * 4 + 3]);
+            o4[q] = x;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) {
+              float g = p.gate ? p.gate[n0 + j] : 1.f;
+              o[j] += g * bf16_round(v[j]);
+            }
+        }
+      } else if (EPI == VCOF_EPI_GATE_ACCUM_BF16) {
+        // W[row, n] = bf16(float(W[row, n]) + gate[n] * acc): in-place LoRA merge (lora_utils.py:496: the weight is
+        // lifted to fp32, updated and cast back)
+        bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + n0;
+        if (full_chunk) {
+          uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 w = o4[q];
+            const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gate + n0) + q * 2);
+            const float4 gb = __ldg(reinterpret_cast<const float4*>(p.gate + n0) + q * 2 + 1);
+            const float2 f0 = __bfloat1622float2(w2[0]), f1 = __bfloat1622float2(w2[1]);
+            const float2 f2 = __bfloat1622float2(w2[2]), f3 = __bfloat1622float2(w2[3]);
+            uint4 r;
+            r.x = pack_bf16x2(f0.x + ga.x * v[q * 8 + 0], f0.y + ga.y * v[q * 8 + 1]);
+            r.y = pack_bf16x2(f1.x + ga.z * v[q * 8 + 2], f1.y + ga.w * v[q * 8 + 3]);
+            r.z = pack_bf16x2(f2.x + gb.x * v[q * 8 + 4], f2.y + gb.y * v[q * 8 + 5]);
+            r.w = pack_bf16x2(f3.x + gb.z * v[q * 8 + 6], f3.y + gb.w * v[q * 8 + 7]);
+            o4[q] = r;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) o[j] = __float2bfloat16_rn(__bfloat162float(o[j]) + p.gate[n0 + j] * v[j]);
+        }
+      } else if (EPI == VCOF_EPI_RAW_F32) {  // out = acc + bias, unrounded (attention scores)
+        float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0;
+        if (full_chunk) {
+          float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            o4[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) o[j] = v[j];
+        }
+      } else {  // VCOF_EPI_BIAS_F32: out = float(bf16(acc + bias))
+        float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0;
+        if (full_chunk) {
+          float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            o4[q] = make_float4(bf16_round(v[q * 4]), bf16_round(v[q * 4 + 1]),
+                                bf16_round(v[q * 4 + 2]), bf16_round(v[q * 4 + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) o[j] = bf16_round(v[j]);
+        }
+      }
+    }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -171,143 +312,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(bar_tfull + 8 * acc, acc_ph);
       tc_fence_after();
       const int row = m_blk * kBM + warp * 32 + lane;
-      const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + ((warp * 32u) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(t_row + c * 32, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const bool full_chunk = (n0 + 32 <= p.N);
-        if (p.bias != nullptr) {
-          if (full_chunk) {
-            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 b = __ldg(bp + q);
-              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 f = __bfloat1622float2(b2[e]);
-                v[q * 8 + e * 2] += f.x;
-                v[q * 8 + e * 2 + 1] += f.y;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) v[j] += __bfloat162float(p.bias[n0 + j]);
-          }
-        }
-        if (EPI == VCOF_EPI_BIAS_GELU_BF16) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(bf16_round(v[j]));
-        }
-        if (!row_ok) continue;
-        if (EPI == VCOF_EPI_BIAS_BF16 || EPI == VCOF_EPI_BIAS_GELU_BF16) {
-          bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + n0;
-          if (full_chunk) {
-            uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 w;
-              w.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-              w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-              w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-              w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-              o4[q] = w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
-          }
-        } else if (EPI == VCOF_EPI_BIAS_GATE_RES_F32) {
-          // x[row, n] += gate[n] * bf16(acc + bias)   (reference :499 / :504 / :511:
-          // the Linear output is a bf16 tensor, the residual stream is fp32)
-          float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0;
-          if (full_chunk) {
-            float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 x = o4[q];
-              float g0 = 1.f, g1 = 1.f, g2 = 1.f, g3 = 1.f;
-              if (p.gate != nullptr) {
-                float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + n0) + q);
-                g0 = g.x; g1 = g.y; g2 = g.z; g3 = g.w;
-              }
-              x.x += g0 * bf16_round(v[q * 4 + 0]);
-              x.y += g1 * bf16_round(v[q * 4 + 1]);
-              x.z += g2 * bf16_round(v[q * 4 + 2]);
-              x.w += g3 * bf16_round(v[q * 4 + 3]);
-              o4[q] = x;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) {
-                float g = p.gate ? p.gate[n0 + j] : 1.f;
-                o[j] += g * bf16_round(v[j]);
-              }
-          }
-        } else if (EPI == VCOF_EPI_GATE_ACCUM_BF16) {
-          // W[row, n] = bf16(float(W[row, n]) + gate[n] * acc): in-place LoRA merge (lora_utils.py:496: the weight is
-          // lifted to fp32, updated and cast back)
-          bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + n0;
-          if (full_chunk) {
-            uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 w = o4[q];
-              const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w);
-              const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gate + n0) + q * 2);
-              const float4 gb = __ldg(reinterpret_cast<const float4*>(p.gate + n0) + q * 2 + 1);
-              const float2 f0 = __bfloat1622float2(w2[0]), f1 = __bfloat1622float2(w2[1]);
-              const float2 f2 = __bfloat1622float2(w2[2]), f3 = __bfloat1622float2(w2[3]);
-              uint4 r;
-              r.x = pack_bf16x2(f0.x + ga.x * v[q * 8 + 0], f0.y + ga.y * v[q * 8 + 1]);
-              r.y = pack_bf16x2(f1.x + ga.z * v[q * 8 + 2], f1.y + ga.w * v[q * 8 + 3]);
-              r.z = pack_bf16x2(f2.x + gb.x * v[q * 8 + 4], f2.y + gb.y * v[q * 8 + 5]);
-              r.w = pack_bf16x2(f3.x + gb.z * v[q * 8 + 6], f3.y + gb.w * v[q * 8 + 7]);
-              o4[q] = r;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) o[j] = __float2bfloat16_rn(__bfloat162float(o[j]) + p.gate[n0 + j] * v[j]);
-          }
-        } else if (EPI == VCOF_EPI_RAW_F32) {  // out = acc + bias, unrounded (attention scores)
-          float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0;
-          if (full_chunk) {
-            float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              o4[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) o[j] = v[j];
-          }
-        } else {  // VCOF_EPI_BIAS_F32: out = float(bf16(acc + bias))
-          float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0;
-          if (full_chunk) {
-            float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              o4[q] = make_float4(bf16_round(v[q * 4]), bf16_round(v[q * 4 + 1]),
-                                  bf16_round(v[q * 4 + 2]), bf16_round(v[q * 4 + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) o[j] = bf16_round(v[j]);
-          }
-        }
-      }
+      gemm_epilogue_tile<BN, EPI>(p, t_row, row, n_blk);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
@@ -320,6 +326,187 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+// ---------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2), 256 x 256 tiles per pair.  EXPERIMENTAL, opt-in with VCOF_GEMM_2CTA=1 — written
+// at the end of round 1 and not yet validated on hardware: the single-CTA kernel needs 48 KB of
+// operands per 512-clock k-block (96 B/clk/SM) against a measured feed of ~77 B/clk/SM; here each CTA stages its own
+// 128 rows of A and only HALF of the 256 rows of B (32 KB per k-block, 64 B/clk/SM), six stages deep.
+//   rank 0 (leader): its MMA lane issues tcgen05.mma.cta_group::2 (M = 256: 128 TMEM lanes in each CTA) after
+//     waiting on ITS full[s], which counts one arrival per CTA plus the TMA bytes of both;
+//   both ranks: TMA producer (own A rows, own half of B), completion bytes go to the leader's full[s];
+//     slot release = the leader's commit, multicast to empty[s] of both CTAs; accumulator-ready likewise (tfull);
+//   both ranks: four epilogue warps drain their own 128 lanes; accumulator-free arrivals all go to the leader's
+//     tempty (count 8).
+// ---------------------------------------------------------------------------
+struct Gemm2Cfg {
+  static constexpr int kBN = 256;
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = kBM * kBK * 2;            // 128 rows of A
+  static constexpr int kBBytes = (kBN / 2) * kBK * 2;      // this CTA's 128 of the 256 B rows
+  static constexpr int kStageBytes = kABytes + kBBytes;    // 32 KB
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+  static constexpr int kTmemCols = 512;                    // two 256-column accumulators
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2cta_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     GemmArgs p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int S = Cfg::kStages;
+  constexpr int BN = Cfg::kBN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + S * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  const uint32_t bar_full = smem_u32(bars);            // used in the leader only
+  const uint32_t bar_empty = bar_full + 8 * S;         // per CTA, arrived by the leader's multicast commit
+  const uint32_t bar_tfull = bar_empty + 8 * S;        // per CTA, multicast commit
+  const uint32_t bar_tempty = bar_tfull + 16;          // leader only, 8 arrivals (4 warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 5) {
+    if (lane == 0) {
+      for (int i = 0; i < S; ++i) {
+        mbar_init(bar_full + 8 * i, 2);
+        mbar_init(bar_empty + 8 * i, 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_tfull + 8 * i, 1);
+        mbar_init(bar_tempty + 8 * i, 8);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair(smem_u32(tmem_slot), Cfg::kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + 2 * kBM - 1) / (2 * kBM);   // 256-row blocks
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 4) {
+    // ---------------- TMA producer (both CTAs) ----------------
+    if (lane == 0) {
+      const uint32_t full_leader = mapa_shared(bar_full, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int m_blk, n_blk;
+        tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
+        const int row_a = (m_blk * 2 + int(rank)) * kBM;
+        const int row_b = n_blk * BN + int(rank) * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * Cfg::kStageBytes);   // arrival 1 of 2 + bytes of both CTAs
+          else mbar_arrive_cluster(full_leader + 8 * s);                          // arrival 2 of 2
+          tma_load_2d_pair(smem_u32(sA + s * Cfg::kABytes), &tmA, full_leader + 8 * s, kb * kBK, row_a);
+          tma_load_2d_pair(smem_u32(sB + s * Cfg::kBBytes), &tmB, full_leader + 8 * s, kb * kBK, row_b);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------- MMA issuer (leader CTA only) ----------------
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kBM, BN, false, false);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const uint64_t a_desc = make_desc_kmajor_sw128(smem_u32(sA + s * Cfg::kABytes));
+          const uint64_t b_desc = make_desc_kmajor_sw128(smem_u32(sB + s * Cfg::kBBytes));
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) umma_ss_pair(d_tmem, a_desc + k * 2, b_desc + k * 2, idesc, (kb | k) != 0);
+          umma_commit_pair(bar_empty + 8 * s);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+        umma_commit_pair(bar_tfull + 8 * acc);
+      }
+    }
+  } else if (warp < 4) {
+    // ---------------- epilogue warps 0..3 (both CTAs, own 128 accumulator rows) ----------------
+    const uint32_t tempty_leader = mapa_shared(bar_tempty, 0);
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      int m_blk, n_blk;
+      tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * acc, acc_ph);
+      tc_fence_after();
+      const int row = (m_blk * 2 + int(rank)) * kBM + warp * 32 + lane;
+      const uint32_t t_row = tmem_base + ((warp * 32u) << 16) + acc * BN;
+      gemm_epilogue_tile<BN, EPI>(p, t_row, row, n_blk);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // neither CTA may retire (or free TMEM) while its peer can still signal it
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int EPI>
+static int launch_gemm2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm2cta_bf16_kernel<EPI>;
+  if (!attr_set) {
+    VCOF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int num_tiles = ((args.M + 2 * kBM - 1) / (2 * kBM)) * ((args.N + Gemm2Cfg::kBN - 1) / Gemm2Cfg::kBN);
+  int grid = 2 * num_tiles < sm_count() ? 2 * num_tiles : (sm_count() & ~1);
+  kern<<<grid, kGemmThreads, Gemm2Cfg::kSmemBytes, stream>>>(tmA, tmB, args);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int dispatch_epi_2cta(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args,
+                             cudaStream_t stream) {
+  switch (epi) {
+    case VCOF_EPI_BIAS_BF16: return launch_gemm2cta<VCOF_EPI_BIAS_BF16>(tmA, tmB, args, stream);
+    case VCOF_EPI_BIAS_GELU_BF16: return launch_gemm2cta<VCOF_EPI_BIAS_GELU_BF16>(tmA, tmB, args, stream);
+    case VCOF_EPI_BIAS_GATE_RES_F32: return launch_gemm2cta<VCOF_EPI_BIAS_GATE_RES_F32>(tmA, tmB, args, stream);
+    default: break;
+  }
+  set_last_error("vcof_gemm_bf16: epilogue %d has no CTA-pair variant", epi);
+  return -1;
 }
 
 template <int BN, int EPI>
@@ -402,6 +589,16 @@ extern "C" int vcof_gemm_bf16(const void* a, long long lda, const void* w, long 
     args.producers = producers;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const bool pair_mode = [] {
+    const char* e = getenv("VCOF_GEMM_2CTA");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (pair_mode && N >= 256 && M >= 256 && epilogue <= VCOF_EPI_BIAS_GATE_RES_F32) {
+    // experimental CTA-pair kernel: B box is this CTA's 128-row half of the 256-row tile
+    rc = make_tmap_2d_bf16(&tmB, w, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, kBK, 128);
+    if (rc) return rc;
+    return dispatch_epi_2cta(epilogue, tmA, tmB, args, st);
+  }
   if (BN == 256) return dispatch_epi<256>(epilogue, tmA, tmB, args, st);
   if (BN == 128) return dispatch_epi<128>(epilogue, tmA, tmB, args, st);
   return dispatch_epi<64>(epilogue, tmA, tmB, args, st);
