@@ -128,6 +128,22 @@ int vcof_conv_igemm(const void* x, const long long* x_dims, const long long* x_s
                     const void* residual, void* out, long long ldc, float clamp, void* act_out,
                     const float* act_gamma, void* stream);
 
+/* EXPERIMENTAL (opt-in, VCOF_CONV_LINES=1 in videocof_b200/vae.py; not yet validated on hardware): the same
+ * stride-1 'same' 3x3 / 3x3x3 convolution as vcof_conv_igemm on channels-last bf16 [T, H, W, C], with input lines
+ * and per-phase weight tiles kept resident in shared memory (csrc/conv_sm100.cu, conv_lines_kernel).
+ *   x, x_dims, x_strides   the plain 5-D view (C, W, 1, H, T) as for vcof_conv_igemm
+ *   w            bf16 [cin/32 * kt * 9, n_total, 32]: slice ((chunk * kt + dt) * 3 + dh) * 3 + dw holds the 32 input
+ *                channels `chunk` of tap (dt, dh, dw) for every output channel
+ *   kt, t0       temporal taps (1 | 3) and the input frame of the first one relative to the output frame
+ *                (-(kt-1) for the causal convolution, plus the halo shift under temporal sharding)
+ *   geom[7]      T_out, H_out, W_out, n_total, n_tile (channels per pass, <= 256), rows (output rows per work item,
+ *                rows * roundup32(n_tile) <= 512), n_store
+ * bias / residual / out / ldc / clamp / act_out / act_gamma as vcof_conv_igemm (plain output addressing).
+ * Replaces CausalConv3d / Conv2d of wan_vae.py:21-40, 190-224 for the 3x3(x3) stride-1 layers. */
+int vcof_conv_lines(const void* x, const long long* x_dims, const long long* x_strides, const void* w, int cin, int kt,
+                    int t0, const int* geom, const float* bias, const void* residual, void* out, long long ldc,
+                    float clamp, void* act_out, const float* act_gamma, void* stream);
+
 /* y = [silu]( x / max(||x||_2, 1e-12) * sqrt(C) * gamma ) per position, channels-last; RMS_norm (+ nn.SiLU)
  * of wan_vae.py:43-58, fp32 intermediates and one bf16 rounding at the store (the reference's ATen chain rounds
  * after every op). */

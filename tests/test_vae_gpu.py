@@ -52,8 +52,12 @@ CONV_CASES = {
 @pytest.mark.parametrize("name", list(CONV_CASES))
 def test_conv_igemm_vs_contract(name, kc, monkeypatch):
     """Both K-slice widths of the kernel (64- and 128-byte TMA rows, SW64 / SW128 descriptors)."""
-    from videocof_b200 import vae
     monkeypatch.setenv("VCOF_CONV_KC", kc)
+    _conv_case(name, monkeypatch)
+
+
+def _conv_case(name, monkeypatch):
+    from videocof_b200 import vae
     c = CONV_CASES[name]
     torch.manual_seed(0)
     conv = vae.CausalConv3d(c["cin"], c["cout"], c["k"], padding=tuple(k // 2 for k in c["k"]))
@@ -68,13 +72,13 @@ def test_conv_igemm_vs_contract(name, kc, monkeypatch):
         norm.gamma.data = (torch.rand_like(norm.gamma) + 0.5).bfloat16().float()
         kw.update(act_norm=norm, want_raw=c.get("raw", True))
     from videocof_b200 import ops
-    real = ops.conv_igemm
+    real = ops.conv_igemm, ops.conv_lines
     # contract (CPU)
-    ops.conv_igemm = emu.conv_igemm
+    ops.conv_igemm, ops.conv_lines = emu.conv_igemm, emu.conv_lines
     try:
         want = vae.conv_causal(x, conv, residual=res, **kw)
     finally:
-        ops.conv_igemm = real
+        ops.conv_igemm, ops.conv_lines = real
     conv_cuda = conv.to("cuda")
     conv_cuda.__dict__.pop("_vcof_pack", None)
     if norm is not None:
@@ -88,6 +92,19 @@ def test_conv_igemm_vs_contract(name, kc, monkeypatch):
         assert (g_ is None) == (w_ is None)
         if g_ is not None:
             assert rel(g_, w_) < 4e-3, rel(g_, w_)
+
+
+LINE_CASES = ["c3x3x3_96_96_res", "c3x3x3_384_384", "c3x3x3_192_384", "c3x3x3_96_96_res_act", "c3x3x3_32_96",
+              "head_96_3_clamp", "c3x3x3_192_384_actonly"]
+
+
+@pytest.mark.skipif(os.environ.get("VCOF_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental line-resident conv kernel (opt-in, not yet validated on hardware)")
+@pytest.mark.parametrize("name", LINE_CASES)
+def test_conv_lines_vs_contract(name, monkeypatch):
+    """vcof_conv_lines (VCOF_CONV_LINES=1) against the same CPU contract as the default kernel."""
+    monkeypatch.setenv("VCOF_CONV_LINES", "1")
+    _conv_case(name, monkeypatch)
 
 
 def test_resamplers_and_norm_vs_contract():

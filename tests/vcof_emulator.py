@@ -92,6 +92,25 @@ def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=Non
     return out if out is not None else act_out
 
 
+def conv_lines(x, x_dims, x_strides, w, cin, kt, t0, geom, bias, out, residual=None, clamp=0.0, act_out=None,
+               act_gamma=None):
+    """Contract of vcof_conv_lines stated through conv_igemm's: the packed weight is re-ordered to the tap-major
+    layout and the 9 * kt taps are spelled out (slice ((chunk*kt + dt)*3 + dh)*3 + dw of the line layout)."""
+    T, H, W, n_total, n_tile, rows, n_store = geom
+    cc = cin // 32
+    w6 = w.view(cc, kt, 3, 3, n_total, 32)                          # [chunk, dt, dh, dw, n, 32]
+    taps, mats = [], []
+    for dh in range(3):
+        for dw in range(3):
+            for dt in range(kt):
+                taps.append((0, dw - 1, 0, dh - 1, t0 + dt))
+                mats.append(w6[:, dt, dh, dw])                      # [chunk, n, 32]
+    wt = torch.stack(mats, dim=0).reshape(len(taps) * cc, n_total, 32).contiguous()   # tgroup = 1: [tap, chunk]
+    g17 = [T, H, W, 1, n_total, n_total, 1, 0, 1, 0, 1, 0, H, W, 0, n_store]
+    return conv_igemm(x, x_dims, x_strides, wt, taps, cin, g17, bias, out, residual=residual, clamp=clamp,
+                      act_out=act_out, act_gamma=act_gamma, tgroup=1)
+
+
 def rms_silu_cl(x, gamma, silu=True, out=None):
     """y = [silu](x / max(||x||, 1e-12) * sqrt(C) * gamma): fp32 intermediates, one rounding at the store."""
     xf = x.float()
@@ -128,6 +147,6 @@ def softmax_rows(s, scale, out=None):
 
 def install(monkeypatch):
     from videocof_b200 import ops, vae
-    for name in ("gemm", "conv_igemm", "rms_silu_cl", "nchw_to_cl", "cl_to_nchw", "softmax_rows"):
+    for name in ("gemm", "conv_igemm", "conv_lines", "rms_silu_cl", "nchw_to_cl", "cl_to_nchw", "softmax_rows"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(vae.AutoencoderKLWan_, "_check", lambda self, x: None)

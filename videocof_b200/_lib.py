@@ -27,6 +27,8 @@ SIGNATURES = {
     "vcof_unpatchify": [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vcof_conv_igemm": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                         c_void_p, c_void_p, c_void_p, c_ll, c_float, c_void_p, c_void_p, c_void_p],
+    "vcof_conv_lines": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                        c_void_p, c_ll, c_float, c_void_p, c_void_p, c_void_p],
     "vcof_rms_silu_cl": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_ll, c_int, c_int, c_void_p],
     "vcof_nchw_to_cl": [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p],
     "vcof_cl_to_nchw": [c_void_p, c_ll, c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p],

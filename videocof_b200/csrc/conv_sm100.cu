@@ -73,6 +73,160 @@ struct ConvArgs {
   const float* act_gamma;     // fp32 [n_store]
 };
 
+// Epilogue of ONE output position (this thread's TMEM lane, n_end accumulator columns starting at t_row):
+// bias (+ residual, clamp) -> bf16 store, and optionally the next layer's RMS_norm + SiLU as a second output.
+__device__ __forceinline__ void conv_epilogue_row(const ConvArgs& p, const float* sBias, const float* sGamma,
+                                                  uint32_t t_row, int t, int h, int w, int n0, int n_end) {
+  const bool ok = (h < p.H_out) && (w < p.W_out);
+  const long long pos_row = (long long)(h * p.oh_mul + p.oh_add) * p.Ws + (w * p.ow_mul + p.ow_add);
+  const int frame = t * p.ot_mul + p.ot_add;
+  // one 32-channel chunk: accumulator + bias (+ residual, clamp) -> v[]; returns #valid channels.
+  // Full chunks (cnt == 32, the common case) run without per-element predicates.
+  auto chunk = [&](int c, float* v, long long& off, int& n) -> int {
+    uint32_t rr[32];
+    tmem_ld32(t_row + c, rr);
+    tmem_ld_wait();
+    n = n0 + c;
+    int fr = frame, ns = n;
+    if (p.interleave_half > 0 && n >= p.interleave_half) { fr += 1; ns = n - p.interleave_half; }
+    off = ((long long)fr * p.Hs * p.Ws + pos_row) * p.ldc + ns;
+    const int cnt = min(32, min(p.n_total - n, (p.interleave_half > 0 ? p.interleave_half : p.n_store) - ns));
+    if (!ok) return 0;
+    const float4* b4 = reinterpret_cast<const float4*>(sBias + n);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = b4[q];                       // channels beyond n_total read zeros of the padding
+      v[q * 4 + 0] = __uint_as_float(rr[q * 4 + 0]) + b.x;
+      v[q * 4 + 1] = __uint_as_float(rr[q * 4 + 1]) + b.y;
+      v[q * 4 + 2] = __uint_as_float(rr[q * 4 + 2]) + b.z;
+      v[q * 4 + 3] = __uint_as_float(rr[q * 4 + 3]) + b.w;
+    }
+    if (p.residual != nullptr) {
+      const bf16* rp = p.residual + off;
+      if (cnt == 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 u = *reinterpret_cast<const uint4*>(rp + q * 8);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h2[e]);
+            // the reference adds two bf16 tensors: round the conv output first
+            v[q * 8 + e * 2] = bf16_round(v[q * 8 + e * 2]) + f.x;
+            v[q * 8 + e * 2 + 1] = bf16_round(v[q * 8 + e * 2 + 1]) + f.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < cnt) v[j] = bf16_round(v[j]) + __bfloat162float(rp[j]);
+      }
+    }
+    if (p.clamp > 0.f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -p.clamp), p.clamp);
+    }
+    return cnt;
+  };
+  auto store = [&](bf16* o, const float* v, int cnt) {
+    if (cnt == 32) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+        u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+        u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+        u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+        *reinterpret_cast<uint4*>(o + q * 8) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < cnt) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  };
+  // activation of one chunk: silu(r * inv * gamma) with r the bf16-rounded result (what the next layer's
+  // RMS_norm reads); fp32 intermediates, ONE rounding at the store
+  auto activate = [&](float* v, int n, int cnt, float inv) {
+    const float4* g4 = reinterpret_cast<const float4*>(sGamma + n);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 g = g4[q];
+      const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = bf16_round(v[q * 4 + e]) * inv * gg[e];
+        v[q * 4 + e] = __fdividef(a, 1.f + __expf(-a));
+      }
+    }
+    (void)cnt;
+  };
+  if (p.act_out == nullptr) {
+#pragma unroll 1
+    for (int c = 0; c < n_end; c += 32) {
+      float v[32];
+      long long off;
+      int n;
+      const int cnt = chunk(c, v, off, n);
+      if (cnt > 0) store(p.out + off, v, cnt);
+    }
+  } else if (n_end <= 128) {
+    // fused RMS_norm + SiLU of the NEXT layer (wan_vae.py:43-58, 197-201): the thread owns the whole channel
+    // row (n_tile == n_total); up to 128 channels stay in registers between the two sweeps
+    float v[4][32];
+    long long off[4];
+    int nn[4], cnt[4];
+    float sq = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+      cnt[ci] = 0;
+      if (ci * 32 < n_end) {
+        cnt[ci] = chunk(ci * 32, v[ci], off[ci], nn[ci]);
+        if (cnt[ci] > 0) {
+          if (p.out != nullptr) store(p.out + off[ci], v[ci], cnt[ci]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < cnt[ci]) { const float r = bf16_round(v[ci][j]); sq += r * r; }
+        }
+      }
+    }
+    const float inv = sqrtf(float(p.n_store)) / fmaxf(sqrtf(sq), 1e-12f);
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+      if (cnt[ci] > 0) {
+        activate(v[ci], nn[ci], cnt[ci], inv);
+        store(p.act_out + off[ci], v[ci], cnt[ci]);
+      }
+    }
+  } else {
+    // wider rows: second sweep over TMEM instead of 384 live registers
+    float sq = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < n_end; c += 32) {
+      float v[32];
+      long long off;
+      int n;
+      const int cnt = chunk(c, v, off, n);
+      if (cnt <= 0) continue;
+      if (p.out != nullptr) store(p.out + off, v, cnt);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < cnt) { const float r = bf16_round(v[j]); sq += r * r; }
+    }
+    const float inv = sqrtf(float(p.n_store)) / fmaxf(sqrtf(sq), 1e-12f);
+#pragma unroll 1
+    for (int c = 0; c < n_end; c += 32) {
+      float v[32];
+      long long off;
+      int n;
+      const int cnt = chunk(c, v, off, n);
+      if (cnt <= 0) continue;
+      activate(v, n, cnt, inv);
+      store(p.act_out + off, v, cnt);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kCvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ ConvArgs p) {
@@ -240,159 +394,203 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tc_fence_after();
       const int r = warp * 32 + lane;
       const int h = h0 + (r >> 4), w = w0 + (r & 15);
-      const bool ok = (h < p.H_out) && (w < p.W_out);
-      const long long pos_row = (long long)(h * p.oh_mul + p.oh_add) * p.Ws + (w * p.ow_mul + p.ow_add);
-      const int frame = t * p.ot_mul + p.ot_add;
-      const uint32_t t_row = tmem_base + ((warp * 32u) << 16) + acc * 256;
-      const int n_end = min(p.n_tile, p.n_total - n0);
-      // one 32-channel chunk: accumulator + bias (+ residual, clamp) -> v[]; returns #valid channels.
-      // Full chunks (cnt == 32, the common case) run without per-element predicates.
-      auto chunk = [&](int c, float* v, long long& off, int& n) -> int {
-        uint32_t rr[32];
-        tmem_ld32(t_row + c, rr);
-        tmem_ld_wait();
-        n = n0 + c;
-        int fr = frame, ns = n;
-        if (p.interleave_half > 0 && n >= p.interleave_half) { fr += 1; ns = n - p.interleave_half; }
-        off = ((long long)fr * p.Hs * p.Ws + pos_row) * p.ldc + ns;
-        const int cnt = min(32, min(p.n_total - n, (p.interleave_half > 0 ? p.interleave_half : p.n_store) - ns));
-        if (!ok) return 0;
-        const float4* b4 = reinterpret_cast<const float4*>(sBias + n);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 b = b4[q];                       // channels beyond n_total read zeros of the padding
-          v[q * 4 + 0] = __uint_as_float(rr[q * 4 + 0]) + b.x;
-          v[q * 4 + 1] = __uint_as_float(rr[q * 4 + 1]) + b.y;
-          v[q * 4 + 2] = __uint_as_float(rr[q * 4 + 2]) + b.z;
-          v[q * 4 + 3] = __uint_as_float(rr[q * 4 + 3]) + b.w;
-        }
-        if (p.residual != nullptr) {
-          const bf16* rp = p.residual + off;
-          if (cnt == 32) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rp + q * 8);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h2[e]);
-                // the reference adds two bf16 tensors: round the conv output first
-                v[q * 8 + e * 2] = bf16_round(v[q * 8 + e * 2]) + f.x;
-                v[q * 8 + e * 2 + 1] = bf16_round(v[q * 8 + e * 2 + 1]) + f.y;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < cnt) v[j] = bf16_round(v[j]) + __bfloat162float(rp[j]);
-          }
-        }
-        if (p.clamp > 0.f) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -p.clamp), p.clamp);
-        }
-        return cnt;
-      };
-      auto store = [&](bf16* o, const float* v, int cnt) {
-        if (cnt == 32) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-            u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-            u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-            u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-            *reinterpret_cast<uint4*>(o + q * 8) = u;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < cnt) o[j] = __float2bfloat16_rn(v[j]);
-        }
-      };
-      // activation of one chunk: silu(r * inv * gamma) with r the bf16-rounded result (what the next layer's
-      // RMS_norm reads); fp32 intermediates, ONE rounding at the store
-      auto activate = [&](float* v, int n, int cnt, float inv) {
-        const float4* g4 = reinterpret_cast<const float4*>(sGamma + n);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 g = g4[q];
-          const float gg[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = bf16_round(v[q * 4 + e]) * inv * gg[e];
-            v[q * 4 + e] = __fdividef(a, 1.f + __expf(-a));
-          }
-        }
-        (void)cnt;
-      };
-      if (p.act_out == nullptr) {
-#pragma unroll 1
-        for (int c = 0; c < n_end; c += 32) {
-          float v[32];
-          long long off;
-          int n;
-          const int cnt = chunk(c, v, off, n);
-          if (cnt > 0) store(p.out + off, v, cnt);
-        }
-      } else if (n_end <= 128) {
-        // fused RMS_norm + SiLU of the NEXT layer (wan_vae.py:43-58, 197-201): the thread owns the whole channel
-        // row (n_tile == n_total); up to 128 channels stay in registers between the two sweeps
-        float v[4][32];
-        long long off[4];
-        int nn[4], cnt[4];
-        float sq = 0.f;
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          cnt[ci] = 0;
-          if (ci * 32 < n_end) {
-            cnt[ci] = chunk(ci * 32, v[ci], off[ci], nn[ci]);
-            if (cnt[ci] > 0) {
-              if (p.out != nullptr) store(p.out + off[ci], v[ci], cnt[ci]);
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < cnt[ci]) { const float r = bf16_round(v[ci][j]); sq += r * r; }
-            }
-          }
-        }
-        const float inv = sqrtf(float(p.n_store)) / fmaxf(sqrtf(sq), 1e-12f);
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          if (cnt[ci] > 0) {
-            activate(v[ci], nn[ci], cnt[ci], inv);
-            store(p.act_out + off[ci], v[ci], cnt[ci]);
-          }
-        }
-      } else {
-        // wider rows: second sweep over TMEM instead of 384 live registers
-        float sq = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < n_end; c += 32) {
-          float v[32];
-          long long off;
-          int n;
-          const int cnt = chunk(c, v, off, n);
-          if (cnt <= 0) continue;
-          if (p.out != nullptr) store(p.out + off, v, cnt);
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < cnt) { const float r = bf16_round(v[j]); sq += r * r; }
-        }
-        const float inv = sqrtf(float(p.n_store)) / fmaxf(sqrtf(sq), 1e-12f);
-#pragma unroll 1
-        for (int c = 0; c < n_end; c += 32) {
-          float v[32];
-          long long off;
-          int n;
-          const int cnt = chunk(c, v, off, n);
-          if (cnt <= 0) continue;
-          activate(v, n, cnt, inv);
-          store(p.act_out + off, v, cnt);
-        }
-      }
+      conv_epilogue_row(p, sBias, sGamma, tmem_base + ((warp * 32u) << 16) + acc * 256, t, h, w, n0,
+                        min(p.n_tile, p.n_total - n0));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Line-resident variant for stride-1 3x3(x3) convolutions.  EXPERIMENTAL, opt-in (VCOF_CONV_LINES=1 in vae.py);
+// written at the end of round 1, not yet validated on hardware.
+//
+// conv_igemm_kernel re-fetches the shifted input patch for every filter tap and the weights for every tile: 146 B of
+// operands per MMA-clock for 96 -> 96 against ~40 B/clk/SM of feed.  Here a tile is ONE output row segment of 128
+// pixels and a CTA works on R consecutive rows at a time (R accumulators side by side in TMEM):
+//   * an input LINE (130 haloed pixels x 32 channels of one row of one frame) is fetched once per (channel slice,
+//     temporal tap) and serves up to nine taps: the three horizontal taps are row-shifted descriptor views of the same
+//     swizzled buffer (valid: profiles/r1_umma_shift_probe.txt), the three vertical taps feed the accumulators of the
+//     rows above / below;
+//   * the nine weight tiles of a (slice, temporal tap) phase stay in shared memory for all R rows (double-buffered
+//     across phases).
+// 96 -> 96, R = 4: 105 KB per phase for 3456 MMA-clocks = 30 B/clk/SM.
+//   warp 4: line producer   warp 6: weight producer   warp 5: MMA issuer   warps 0-3: epilogue, one row at a time
+// ---------------------------------------------------------------------------
+constexpr int kLnPix = 130;                          // 128 outputs + one halo pixel each side
+constexpr int kLnBytes = 17 * 512;                   // 130 x 64 B rounded up to the SW64 repeat (8704)
+constexpr int kLnMaxRows = 4;
+constexpr int kLnMaxRing = 8;
+
+struct LineArgs {
+  ConvArgs c;          // geometry / epilogue fields (taps unused); c.n_tile = channels per N pass
+  int kt, t0;          // temporal taps and the offset of the first one: t_in = t + t0 + dt
+  int rows;            // R: output rows per CTA work item (rows * n_tile <= 512)
+  int ring;            // line ring depth
+};
+
+__global__ void __launch_bounds__(kCvThreads, 1)
+conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ LineArgs a) {
+  const ConvArgs& p = a.c;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCvData);
+  const uint32_t bar_wfull = smem_u32(bars);                     // [2]
+  const uint32_t bar_wempty = bar_wfull + 16;                    // [2]
+  const uint32_t bar_lfull = bar_wempty + 16;                    // [kLnMaxRing]
+  const uint32_t bar_lempty = bar_lfull + 8 * kLnMaxRing;        // [kLnMaxRing]
+  const uint32_t bar_tfull = bar_lempty + 8 * kLnMaxRing;        // [kLnMaxRows]
+  const uint32_t bar_tempty = bar_tfull + 8 * kLnMaxRows;        // [kLnMaxRows]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * kLnMaxRing + 2 * kLnMaxRows);
+  float* sBias = reinterpret_cast<float*>(smem + kCvData + 512);
+  float* sGamma = sBias + kCvVecMax;
+  for (int i = threadIdx.x; i < kCvVecMax; i += kCvThreads) {
+    sBias[i] = (p.bias != nullptr && i < p.n_total) ? __ldg(p.bias + i) : 0.f;
+    sGamma[i] = (p.act_gamma != nullptr && i < p.n_store) ? __ldg(p.act_gamma + i) : 0.f;
+  }
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const int R = a.rows;
+  if (warp == 4 && lane == 0) tma_prefetch_desc(&tmX);
+  if (warp == 6 && lane == 0) tma_prefetch_desc(&tmW);
+  if (warp == 5) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wempty + 8 * i, 1); }
+      for (int i = 0; i < kLnMaxRing; ++i) { mbar_init(bar_lfull + 8 * i, 1); mbar_init(bar_lempty + 8 * i, 1); }
+      for (int i = 0; i < kLnMaxRows; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int w_bytes = 9 * p.n_tile * 64;                         // nine [n_tile x 32 ch] tiles of one phase
+  const int acc_stride = (p.n_tile + 31) & ~31;                  // TMEM columns per row accumulator
+  const uint32_t smem_w = smem_u32(smem);                        // two weight buffers
+  const uint32_t smem_l = smem_w + 2 * w_bytes;                  // then the line ring (w_bytes is a multiple of 512)
+  const int wsegs = (p.W_out + 127) / 128, hgroups = (p.H_out + R - 1) / R;
+  const int n_passes = (p.n_total + p.n_tile - 1) / p.n_tile;
+  const int num_items = p.T_out * hgroups * wsegs * n_passes;
+  const int phases = p.cin_chunks * a.kt;
+  auto decode = [&](int item, int& t, int& h0, int& w0, int& n0) {
+    n0 = (item % n_passes) * p.n_tile;
+    int s2 = item / n_passes;
+    w0 = (s2 % wsegs) * 128;
+    s2 /= wsegs;
+    h0 = (s2 % hgroups) * R;
+    t = s2 / hgroups;
+  };
+
+  if (warp == 4) {
+    if (lane == 0) {            // ---- line producer ----
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int t, h0, w0, n0;
+        decode(item, t, h0, w0, n0);
+        for (int cc = 0; cc < p.cin_chunks; ++cc)
+          for (int dt = 0; dt < a.kt; ++dt) {
+            const int ct = t + a.t0 + dt;
+            for (int r = 0; r < R + 2; ++r) {
+              const uint32_t dst = smem_l + s * kLnBytes;
+              mbar_wait(bar_lempty + 8 * s, ph ^ 1);
+              mbar_expect_tx(bar_lfull + 8 * s, kLnPix * 64);
+              tma_load_5d(dst, &tmX, bar_lfull + 8 * s, cc * 32, w0 - 1, 0, h0 - 1 + r, ct);
+              if (++s == a.ring) { s = 0; ph ^= 1; }
+            }
+          }
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0) {            // ---- weight producer ----
+      int b = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int t, h0, w0, n0;
+        decode(item, t, h0, w0, n0);
+        for (int phase = 0; phase < phases; ++phase) {
+          mbar_wait(bar_wempty + 8 * b, ph ^ 1);
+          mbar_expect_tx(bar_wfull + 8 * b, w_bytes);
+          tma_load_3d(smem_w + b * w_bytes, &tmW, bar_wfull + 8 * b, 0, n0, phase * 9);
+          if (++b == 2) { b = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {            // ---- MMA issuer ----
+      const uint32_t idesc = make_idesc_bf16(128, p.n_tile, false, false);
+      const uint64_t dflags = kDescVersion1 | kDescSwizzle64 | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 16);
+      const uint64_t wdesc0 = dflags | uint64_t((smem_w & 0x3FFFF) >> 4);
+      const uint64_t ldesc0 = dflags | uint64_t((smem_l & 0x3FFFF) >> 4);
+      const uint32_t w_tile = (p.n_tile * 64) >> 4;              // one (dh, dw) weight tile, in 16-byte units
+      int s = 0, b = 0, it = 0;
+      uint32_t lph = 0, wph = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        for (int phase = 0; phase < phases; ++phase) {
+          const uint64_t wdesc = wdesc0 + uint32_t(b) * (uint32_t(w_bytes) >> 4);
+          mbar_wait(bar_wfull + 8 * b, wph);
+          for (int r = 0; r < R + 2; ++r) {
+            const uint64_t ldesc = ldesc0 + uint32_t(s) * (kLnBytes >> 4);
+            mbar_wait(bar_lfull + 8 * s, lph);
+            tc_fence_after();
+#pragma unroll
+            for (int dh = 0; dh < 3; ++dh) {
+              const int j = r - dh;                              // output row this line feeds through vertical tap dh
+              if (j < 0 || j >= R) continue;
+              const bool first = (phase == 0) && (dh == 0);      // first MMA ever into accumulator j of this item
+              if (first) {
+                mbar_wait(bar_tempty + 8 * j, (it & 1) ^ 1);     // epilogue of the previous item has drained row j
+                tc_fence_after();
+              }
+              const uint32_t d_tmem = tmem_base + j * acc_stride;
+#pragma unroll
+              for (int dw = 0; dw < 3; ++dw) {
+                // horizontal tap = the same line read dw pixels (64-byte rows) further in
+                const uint64_t ad = ldesc + dw * 4;
+                const uint64_t bd = wdesc + (dh * 3 + dw) * w_tile;
+                umma_ss(d_tmem, ad, bd, idesc, !(first && dw == 0));
+                umma_ss(d_tmem, ad + 2, bd + 2, idesc, 1);
+              }
+              if (phase == phases - 1 && dh == 2) umma_commit(bar_tfull + 8 * j);   // row j is complete
+            }
+            umma_commit(bar_lempty + 8 * s);
+            if (++s == a.ring) { s = 0; lph ^= 1; }
+          }
+          umma_commit(bar_wempty + 8 * b);
+          if (++b == 2) { b = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 4) {        // ---- epilogue: rows drain one by one as they complete ----
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      int t, h0, w0, n0;
+      decode(item, t, h0, w0, n0);
+      const int n_end = min(p.n_tile, p.n_total - n0);
+      const int w = w0 + warp * 32 + lane;
+      for (int j = 0; j < R; ++j) {
+        mbar_wait(bar_tfull + 8 * j, it & 1);
+        tc_fence_after();
+        if (h0 + j < p.H_out)
+          conv_epilogue_row(p, sBias, sGamma, tmem_base + ((warp * 32u) << 16) + j * acc_stride, t, h0 + j, w, n0, n_end);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * j);
+      }
     }
   }
 
@@ -603,6 +801,64 @@ extern "C" int vcof_conv_igemm(const void* x, const long long* x_dims, const lon
   VCOF_REQUIRE(tiles > 0 && tiles < (1ll << 31), "vcof_conv_igemm: bad tile count %lld", tiles);
   const int grid = tiles < sm_count() ? (int)tiles : sm_count();
   conv_igemm_kernel<<<grid, kCvThreads, kCvSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW, a);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vcof_conv_lines(const void* x, const long long* x_dims, const long long* x_strides, const void* w,
+                               int cin, int kt, int t0, const int* geom, const float* bias, const void* residual,
+                               void* out, long long ldc, float clamp, void* act_out, const float* act_gamma,
+                               void* stream) {
+  // geom[7]: T_out, H_out, W_out, n_total, n_tile, rows, n_store
+  VCOF_REQUIRE(cin > 0 && cin % 32 == 0, "vcof_conv_lines: cin %d must be a positive multiple of 32", cin);
+  VCOF_REQUIRE(kt == 1 || kt == 3, "vcof_conv_lines: kt %d must be 1 or 3", kt);
+  LineArgs a;
+  ConvArgs& c = a.c;
+  c.ntaps = 9 * kt; c.cin_chunks = cin / 32; c.cin = cin; c.kc = 32;
+  c.T_out = geom[0]; c.H_out = geom[1]; c.W_out = geom[2]; c.t_stride = 1;
+  c.n_total = geom[3]; c.n_tile = geom[4];
+  c.ot_mul = 1; c.ot_add = 0; c.oh_mul = 1; c.oh_add = 0; c.ow_mul = 1; c.ow_add = 0;
+  c.Hs = geom[1]; c.Ws = geom[2];
+  c.ldc = ldc; c.interleave_half = 0; c.n_store = geom[6];
+  c.stages = 0; c.stage_bytes = 0; c.producers = 2; c.tgroup = 1;
+  c.bias = bias; c.residual = reinterpret_cast<const bf16*>(residual); c.out = reinterpret_cast<bf16*>(out);
+  c.clamp = clamp; c.act_out = reinterpret_cast<bf16*>(act_out); c.act_gamma = act_gamma;
+  a.kt = kt; a.t0 = t0; a.rows = geom[5];
+  VCOF_REQUIRE(out != nullptr || act_out != nullptr, "vcof_conv_lines: no output requested");
+  VCOF_REQUIRE(act_out == nullptr || (act_gamma != nullptr && c.n_tile == c.n_total),
+               "vcof_conv_lines: fused norm needs gamma and a single channel pass");
+  VCOF_REQUIRE(c.n_total <= kCvVecMax && c.n_total % 16 == 0 && c.n_tile % 16 == 0 && c.n_tile >= 16 && c.n_tile <= 256,
+               "vcof_conv_lines: n_total %d / n_tile %d must be multiples of 16, n_tile <= 256", c.n_total, c.n_tile);
+  VCOF_REQUIRE(a.rows >= 1 && a.rows <= kLnMaxRows && a.rows * ((c.n_tile + 31) & ~31) <= 512,
+               "vcof_conv_lines: %d rows of %d channels do not fit 512 TMEM columns", a.rows, c.n_tile);
+  VCOF_REQUIRE(ldc % 8 == 0, "vcof_conv_lines: ldc must be a multiple of 8");
+  const int w_bytes = 9 * c.n_tile * 64;
+  a.ring = (kCvData - 2 * w_bytes) / kLnBytes;
+  if (a.ring > kLnMaxRing) a.ring = kLnMaxRing;
+  VCOF_REQUIRE(a.ring >= 3, "vcof_conv_lines: %d-channel passes leave no room for the line ring", c.n_tile);
+  CUtensorMap tmX, tmW;
+  uint64_t dims[5], strides[4];
+  for (int i = 0; i < 5; ++i) dims[i] = (uint64_t)x_dims[i];
+  for (int i = 0; i < 4; ++i) strides[i] = (uint64_t)x_strides[i] * 2;
+  const uint32_t box[5] = {32, (uint32_t)kLnPix, 1, 1, 1};
+  int rc = make_tmap_nd_bf16(&tmX, x, 5, dims, strides, box, 64);
+  if (rc) return rc;
+  // weights: [slices, n_total, 32] with slice = ((chunk * kt + dt) * 3 + dh) * 3 + dw
+  uint64_t wd[3] = {32, (uint64_t)c.n_total, (uint64_t)(c.cin_chunks * kt * 9)};
+  uint64_t ws[2] = {64, (uint64_t)c.n_total * 64};
+  uint32_t wb[3] = {32, (uint32_t)c.n_tile, 9};
+  rc = make_tmap_nd_bf16(&tmW, w, 3, wd, ws, wb, 64);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VCOF_CHECK_CUDA(cudaFuncSetAttribute(conv_lines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem));
+    attr_set = true;
+  }
+  const long long items = (long long)c.T_out * ((c.H_out + a.rows - 1) / a.rows) * ((c.W_out + 127) / 128) *
+                          ((c.n_total + c.n_tile - 1) / c.n_tile);
+  VCOF_REQUIRE(items > 0 && items < (1ll << 31), "vcof_conv_lines: bad item count %lld", items);
+  const int grid = items < sm_count() ? (int)items : sm_count();
+  conv_lines_kernel<<<grid, kCvThreads, kCvSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW, a);
   VCOF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

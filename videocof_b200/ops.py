@@ -294,6 +294,34 @@ def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=Non
     return ref_out
 
 
+def conv_lines(x, x_dims, x_strides, w, cin, kt, t0, geom, bias, out, residual=None, clamp=0.0, act_out=None,
+               act_gamma=None):
+    """Raw binding of vcof_conv_lines (experimental line-resident 3x3(x3) convolution, include/vcof.h).
+    w: packed [cin/32 * kt * 9, n_total, 32]; geom: T_out, H_out, W_out, n_total, n_tile, rows, n_store."""
+    _chk(x, torch.bfloat16, "conv_lines.x")
+    _chk(w, torch.bfloat16, "conv_lines.w", 3)
+    ref_out = out if out is not None else act_out
+    _chk(ref_out, torch.bfloat16, "conv_lines.out")
+    if act_out is not None:
+        _chk(act_out, torch.bfloat16, "conv_lines.act_out")
+        _chk(act_gamma, torch.float32, "conv_lines.act_gamma", 1)
+        if out is not None and act_out.stride(-2) != out.stride(-2):
+            raise _lib.VcofError("conv_lines: out and act_out must share the position pitch")
+    if bias is not None:
+        _chk(bias, torch.float32, "conv_lines.bias", 1)
+    if residual is not None:
+        _chk(residual, torch.bfloat16, "conv_lines.residual")
+    if w.shape[0] != (cin // 32) * kt * 9 or w.shape[2] != 32:
+        raise _lib.VcofError(f"conv_lines: weight pack {tuple(w.shape)} does not match cin={cin}, kt={kt}")
+    _call("vcof_conv_lines", x.data_ptr(), _arr(_ct.c_longlong, [int(v) for v in x_dims]),
+          _arr(_ct.c_longlong, [int(v) for v in x_strides]), w.data_ptr(), cin, int(kt), int(t0),
+          _arr(_ct.c_int, [int(v) for v in geom]), _p(bias), _p(residual), _p(out), ref_out.stride(-2), float(clamp),
+          _p(act_out), _p(act_gamma), _stream(),
+          key=f"conv_lines kt={kt} cin={cin} n={geom[3]} T={geom[0]} H={geom[1]} W={geom[2]}"
+              + ("+act" if act_out is not None else ""))
+    return ref_out
+
+
 def rms_silu_cl(x, gamma, silu=True, out=None):
     """Channels-last RMS_norm (+SiLU).  x bf16 [..., C] contiguous rows; gamma fp32 [C]."""
     _chk(x, torch.bfloat16, "rms_silu.x")

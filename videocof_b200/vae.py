@@ -220,6 +220,40 @@ def pack_conv(conv):
     return _cached(conv, "plain" + os.environ.get("VCOF_CONV_KC", ""), _ver(conv.weight, conv.bias), build)
 
 
+def pack_conv_lines(conv):
+    """Weight pack of the experimental line-resident kernel (vcof_conv_lines): bf16 [cin_p/32 * kt * 9, Cout_p16, 32]
+    with slice ((chunk * kt + dt) * 3 + dh) * 3 + dw; returns (pw, bias, cin_p, kt)."""
+    def build():
+        w = conv.weight.detach().float()
+        if w.dim() == 4:
+            w = w.unsqueeze(2)
+        cout, cin, kt = w.shape[0], w.shape[1], w.shape[2]
+        cin_p, cout_p = _pad32(cin), _pad16(cout)
+        wp = torch.zeros((cout_p, cin_p, kt, 3, 3), dtype=torch.float32, device=w.device)
+        wp[:cout, :cin] = w
+        wp = wp.view(cout_p, cin_p // 32, 32, kt, 3, 3).permute(1, 3, 4, 5, 0, 2)       # [chunk, dt, dh, dw, n, 32]
+        b = torch.zeros(cout_p, dtype=torch.float32, device=w.device)
+        if conv.bias is not None:
+            b[:cout] = conv.bias.detach().float()
+        return wp.reshape(-1, cout_p, 32).to(torch.bfloat16).contiguous(), b, cin_p, kt
+    return _cached(conv, "lines", _ver(conv.weight, conv.bias), build)
+
+
+def _lines_plan(n_total):
+    """(n_tile, rows) of vcof_conv_lines: channels per pass and output rows per work item (rows accumulators of
+    roundup32(n_tile) TMEM columns each, 512 in total), favouring weight reuse over rows."""
+    if n_total <= 128:
+        n_tile = n_total
+    elif n_total % 128 == 0:
+        n_tile = 128
+    elif n_total % 96 == 0:
+        n_tile = 96
+    else:
+        n_tile = 64 if n_total % 64 == 0 else 16
+    rows = max(1, min(4, 512 // ((n_tile + 31) // 32 * 32)))
+    return n_tile, rows
+
+
 def pack_upsample_conv(conv):
     """Fold nearest-2x + Conv2d 3x3 (pad 1) into four parity 2x2 convolutions on the low-res input.
 
@@ -353,12 +387,14 @@ def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None, act_norm=None, 
 
     act_norm: an RMS_norm module whose norm+SiLU (the opening of the NEXT layer) is fused into the epilogue;
     returns (raw, act) then (raw is None when want_raw is False)."""
-    pw, pb, cin_p, tg = pack_conv(conv)
     T, H, W, C = x.shape
     if C != _pad32(conv.weight.shape[1]):
         raise VcofError(f"conv input has {C} channels, the layer expects {_pad32(conv.weight.shape[1])}")
     k = conv.kernel_size
     kt, kh, kw = (1, k[0], k[1]) if len(k) == 2 else k
+    if os.environ.get("VCOF_CONV_LINES") == "1" and kh == 3 and kw == 3 and kt in (1, 3):
+        return _conv_causal_lines(x, conv, kt, residual, clamp, n_store, act_norm, want_raw)
+    pw, pb, cin_p, tg = pack_conv(conv)
     t_shift = 0
     xin = x
     if _SHARD is not None and kt > 1:
@@ -382,6 +418,37 @@ def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None, act_norm=None, 
         return out, act
     out = _alloc(T, H, W, ldc, x.device, zero=(ldc != ns))
     ops.conv_igemm(xin, dims, strides, pw, taps, cin_p, geom, pb, out, residual=residual, clamp=clamp, tgroup=tg)
+    if act_norm is not None:
+        return out, rms_silu(out, act_norm)
+    return out
+
+
+def _conv_causal_lines(x, conv, kt, residual, clamp, n_store, act_norm, want_raw):
+    """conv_causal through the experimental line-resident kernel (opt-in, VCOF_CONV_LINES=1)."""
+    pw, pb, cin_p, _ = pack_conv_lines(conv)
+    T, H, W, C = x.shape
+    t_shift = 0
+    xin = x
+    if _SHARD is not None and kt > 1:
+        xin = _haloed(x)
+        _SHARD.exchange(xin)
+        t_shift = TimeShard.HALO
+    n_total = pw.shape[1]
+    ns = n_total if n_store is None else n_store
+    ldc = (ns + 7) // 8 * 8
+    dims, strides = _view5(xin)
+    n_tile, rows = _lines_plan(n_total)
+    fuse = act_norm is not None and n_tile == n_total
+    geom = [T, H, W, n_total, n_tile, rows, ns]
+    t0 = -(kt - 1) + t_shift
+    if fuse:
+        out = _alloc(T, H, W, ldc, x.device) if want_raw else None
+        act = _alloc(T, H, W, ldc, x.device)
+        ops.conv_lines(xin, dims, strides, pw, cin_p, kt, t0, geom, pb, out, residual=residual, clamp=clamp,
+                       act_out=act, act_gamma=_vec(act_norm, "gamma", act_norm.gamma))
+        return out, act
+    out = _alloc(T, H, W, ldc, x.device, zero=(ldc != ns))
+    ops.conv_lines(xin, dims, strides, pw, cin_p, kt, t0, geom, pb, out, residual=residual, clamp=clamp)
     if act_norm is not None:
         return out, rms_silu(out, act_norm)
     return out
