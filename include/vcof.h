@@ -128,8 +128,8 @@ int vcof_conv_igemm(const void* x, const long long* x_dims, const long long* x_s
                     const void* residual, void* out, long long ldc, float clamp, void* act_out,
                     const float* act_gamma, void* stream);
 
-/* EXPERIMENTAL (opt-in, VCOF_CONV_LINES=1 in videocof_b200/vae.py; not yet validated on hardware): the same
- * stride-1 'same' 3x3 / 3x3x3 convolution as vcof_conv_igemm on channels-last bf16 [T, H, W, C], with input lines
+/* Line-resident kernel (videocof_b200/vae.py routes layers of up to 128 output channels here; VCOF_CONV_LINES=0|1
+ * overrides): the same stride-1 'same' 3x3 / 3x3x3 convolution as vcof_conv_igemm on channels-last bf16 [T, H, W, C], with input lines
  * and per-phase weight tiles kept resident in shared memory (csrc/conv_sm100.cu, conv_lines_kernel).
  *   x, x_dims, x_strides   the plain 5-D view (C, W, 1, H, T) as for vcof_conv_igemm
  *   w            bf16 [cin/32 * kt * 9, n_total, 32]: slice ((chunk * kt + dt) * 3 + dh) * 3 + dw holds the 32 input

@@ -51,8 +51,9 @@ CONV_CASES = {
 @pytest.mark.parametrize("kc", ["32", "64"])
 @pytest.mark.parametrize("name", list(CONV_CASES))
 def test_conv_igemm_vs_contract(name, kc, monkeypatch):
-    """Both K-slice widths of the kernel (64- and 128-byte TMA rows, SW64 / SW128 descriptors)."""
+    """Both K-slice widths of the tap-streaming kernel (64- and 128-byte TMA rows, SW64 / SW128 descriptors)."""
     monkeypatch.setenv("VCOF_CONV_KC", kc)
+    monkeypatch.setenv("VCOF_CONV_LINES", "0")
     _conv_case(name, monkeypatch)
 
 
@@ -72,13 +73,13 @@ def _conv_case(name, monkeypatch):
         norm.gamma.data = (torch.rand_like(norm.gamma) + 0.5).bfloat16().float()
         kw.update(act_norm=norm, want_raw=c.get("raw", True))
     from videocof_b200 import ops
-    real = ops.conv_igemm, ops.conv_lines
+    real = ops.conv_igemm, ops.conv_lines, ops.rms_silu_cl
     # contract (CPU)
-    ops.conv_igemm, ops.conv_lines = emu.conv_igemm, emu.conv_lines
+    ops.conv_igemm, ops.conv_lines, ops.rms_silu_cl = emu.conv_igemm, emu.conv_lines, emu.rms_silu_cl
     try:
         want = vae.conv_causal(x, conv, residual=res, **kw)
     finally:
-        ops.conv_igemm, ops.conv_lines = real
+        ops.conv_igemm, ops.conv_lines, ops.rms_silu_cl = real
     conv_cuda = conv.to("cuda")
     conv_cuda.__dict__.pop("_vcof_pack", None)
     if norm is not None:
@@ -98,8 +99,6 @@ LINE_CASES = ["c3x3x3_96_96_res", "c3x3x3_384_384", "c3x3x3_192_384", "c3x3x3_96
               "head_96_3_clamp", "c3x3x3_192_384_actonly"]
 
 
-@pytest.mark.skipif(os.environ.get("VCOF_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental line-resident conv kernel (opt-in, not yet validated on hardware)")
 @pytest.mark.parametrize("name", LINE_CASES)
 def test_conv_lines_vs_contract(name, monkeypatch):
     """vcof_conv_lines (VCOF_CONV_LINES=1) against the same CPU contract as the default kernel."""
@@ -110,7 +109,7 @@ def test_conv_lines_vs_contract(name, monkeypatch):
 def test_resamplers_and_norm_vs_contract():
     from videocof_b200 import ops, vae
     torch.manual_seed(1)
-    names = ("gemm", "conv_igemm", "rms_silu_cl", "softmax_rows")
+    names = ("gemm", "conv_igemm", "conv_lines", "rms_silu_cl", "softmax_rows")
     real = {n: getattr(ops, n) for n in names}
     for mode, cin in (("downsample2d", 96), ("downsample3d", 192), ("upsample3d", 384), ("upsample2d", 192)):
         rs = vae.Resample(cin, mode)

@@ -411,8 +411,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------
-// Line-resident variant for stride-1 3x3(x3) convolutions.  EXPERIMENTAL, opt-in (VCOF_CONV_LINES=1 in vae.py);
-// written at the end of round 1, not yet validated on hardware.
+// Line-resident variant for stride-1 3x3(x3) convolutions (vae.py uses it for layers of up to 128 output channels;
+// VCOF_CONV_LINES=0|1 overrides).  Parity-green on B200 against the same contract as conv_igemm_kernel
+// (tests/test_vae_gpu.py, profiles/r1_gpurun36_final_validation_lines.log); first version, untuned.
 //
 // conv_igemm_kernel re-fetches the shifted input patch for every filter tap and the weights for every tile: 146 B of
 // operands per MMA-clock for 96 -> 96 against ~40 B/clk/SM of feed.  Here a tile is ONE output row segment of 128

@@ -296,7 +296,7 @@ def conv_igemm(x, x_dims, x_strides, w, taps, cin, geom, bias, out, residual=Non
 
 def conv_lines(x, x_dims, x_strides, w, cin, kt, t0, geom, bias, out, residual=None, clamp=0.0, act_out=None,
                act_gamma=None):
-    """Raw binding of vcof_conv_lines (experimental line-resident 3x3(x3) convolution, include/vcof.h).
+    """Raw binding of vcof_conv_lines (line-resident 3x3(x3) convolution, include/vcof.h).
     w: packed [cin/32 * kt * 9, n_total, 32]; geom: T_out, H_out, W_out, n_total, n_tile, rows, n_store."""
     _chk(x, torch.bfloat16, "conv_lines.x")
     _chk(w, torch.bfloat16, "conv_lines.w", 3)

@@ -221,7 +221,7 @@ def pack_conv(conv):
 
 
 def pack_conv_lines(conv):
-    """Weight pack of the experimental line-resident kernel (vcof_conv_lines): bf16 [cin_p/32 * kt * 9, Cout_p16, 32]
+    """Weight pack of the line-resident kernel (vcof_conv_lines): bf16 [cin_p/32 * kt * 9, Cout_p16, 32]
     with slice ((chunk * kt + dt) * 3 + dh) * 3 + dw; returns (pw, bias, cin_p, kt)."""
     def build():
         w = conv.weight.detach().float()
@@ -392,7 +392,7 @@ def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None, act_norm=None, 
         raise VcofError(f"conv input has {C} channels, the layer expects {_pad32(conv.weight.shape[1])}")
     k = conv.kernel_size
     kt, kh, kw = (1, k[0], k[1]) if len(k) == 2 else k
-    if os.environ.get("VCOF_CONV_LINES") == "1" and kh == 3 and kw == 3 and kt in (1, 3):
+    if kh == 3 and kw == 3 and kt in (1, 3) and _use_lines(conv):
         return _conv_causal_lines(x, conv, kt, residual, clamp, n_store, act_norm, want_raw)
     pw, pb, cin_p, tg = pack_conv(conv)
     t_shift = 0
@@ -423,8 +423,21 @@ def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None, act_norm=None, 
     return out
 
 
+def _use_lines(conv):
+    """Which kernel runs a stride-1 3x3(x3) layer.  Default ("auto"): the line-resident kernel for layers of up to 128
+    output channels (one channel pass, fused norm kept: 1.3-1.9x faster at 96 channels, profiles/
+    r1_gpurun36_final_validation_lines.log), the tap-streaming kernel for wider ones (several passes would re-stream the
+    lines and drop the fused RMS_norm+SiLU).  VCOF_CONV_LINES=1 / 0 forces it on for every eligible layer / off."""
+    mode = os.environ.get("VCOF_CONV_LINES", "auto")
+    if mode == "1":
+        return True
+    if mode == "0":
+        return False
+    return _pad16(conv.weight.shape[0]) <= 128
+
+
 def _conv_causal_lines(x, conv, kt, residual, clamp, n_store, act_norm, want_raw):
-    """conv_causal through the experimental line-resident kernel (opt-in, VCOF_CONV_LINES=1)."""
+    """conv_causal through the line-resident kernel (vcof_conv_lines)."""
     pw, pb, cin_p, _ = pack_conv_lines(conv)
     T, H, W, C = x.shape
     t_shift = 0
