@@ -144,3 +144,75 @@ def load_reference():
     ns = types.SimpleNamespace(dit=dit, vae=vae, unipc=unipc)
     _cache["ns"] = ns
     return ns
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The caller of the hot path: videox_fun/pipeline/pipeline_wan.py, executed unmodified.  It needs a few more
+# diffusers names (DiffusionPipeline, randn_tensor, VideoProcessor …).  The stand-ins below restate only the
+# behaviour WanPipeline.__call__ touches; randn_tensor follows diffusers' published semantics (draw on the
+# generator's device, then move).  The file brackets the DiT call with `torch.cuda.device(device)`, which
+# rejects a CPU device, so the loader swaps that context manager for a null one while the pipeline runs on CPU.
+# ------------------------------------------------------------------------------------------------------------
+class _DiffusionPipeline:
+    def register_modules(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    @property
+    def _execution_device(self):
+        return torch.device("cpu")
+
+    def progress_bar(self, total=None):
+        import contextlib
+
+        class _Bar:
+            def update(self, *_a):
+                pass
+        return contextlib.nullcontext(_Bar())
+
+    def maybe_free_model_hooks(self):
+        pass
+
+
+def _randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
+    gen = generator[0] if isinstance(generator, (list, tuple)) else generator
+    device = torch.device(device or "cpu")
+    rand_device = device
+    if gen is not None and gen.device.type != device.type and gen.device.type == "cpu":
+        rand_device = torch.device("cpu")
+    return torch.randn(shape, generator=gen, device=rand_device, dtype=dtype).to(device)
+
+
+def load_reference_pipeline():
+    """-> namespace with .pipeline (pipeline_wan module), .t5 (wan_text_encoder module) and the models of
+    load_reference()."""
+    if "pipe" in _cache:
+        return _cache["pipe"]
+    import contextlib
+    ns = load_reference()
+    d = sys.modules["diffusers"]
+    d.FlowMatchEulerDiscreteScheduler = type("FlowMatchEulerDiscreteScheduler", (), {})
+    _mod("diffusers.callbacks", MultiPipelineCallbacks=type("MultiPipelineCallbacks", (), {}),
+         PipelineCallback=type("PipelineCallback", (), {}))
+    _mod("diffusers.pipelines")
+    _mod("diffusers.pipelines.pipeline_utils", DiffusionPipeline=_DiffusionPipeline)
+    u = sys.modules["diffusers.utils"]
+    u.BaseOutput = type("BaseOutput", (), {})
+    u.replace_example_docstring = lambda _doc: (lambda f: f)
+    _mod("diffusers.utils.torch_utils", randn_tensor=_randn_tensor)
+    _mod("diffusers.video_processor", VideoProcessor=lambda **_k: None)
+    t5 = _load("videox_fun.models.wan_text_encoder", "videox_fun/models/wan_text_encoder.py")
+    m = sys.modules["videox_fun.models"]
+    m.AutoencoderKLWan, m.WanTransformer3DModel = ns.vae.AutoencoderKLWan, ns.dit.WanTransformer3DModel
+    m.WanT5EncoderModel, m.AutoTokenizer, m.CLIPModel = t5.WanT5EncoderModel, None, None
+    _mod("videox_fun.utils.fm_solvers", FlowDPMSolverMultistepScheduler=type("FlowDPMSolverMultistepScheduler", (), {}),
+         get_sampling_sigmas=None)
+    sys.modules["videox_fun.utils.fm_solvers_unipc"] = ns.unipc
+    p = _mod("videox_fun.pipeline")
+    p.__path__ = []
+    pipe = _load("videox_fun.pipeline.pipeline_wan", "videox_fun/pipeline/pipeline_wan.py")
+    if not torch.cuda.is_available():
+        torch.cuda.device = lambda *a, **k: contextlib.nullcontext()
+    out = types.SimpleNamespace(pipeline=pipe, t5=t5, dit=ns.dit, vae=ns.vae, unipc=ns.unipc)
+    _cache["pipe"] = out
+    return out
