@@ -45,6 +45,17 @@ class _ConfigMixin:
 
 
 class _ModelMixin(nn.Module):
+    def __getattr__(self, name):
+        """diffusers' ModelMixin resolves unknown attributes through the registered config
+        (e.g. vae.spatial_compression_ratio, pipeline_wan.py:138)."""
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            cfg = self.__dict__.get("_vcof_cfg")
+            if cfg is not None and name in cfg:
+                return cfg[name]
+            raise
+
     @property
     def dtype(self):
         return next(self.parameters()).dtype
