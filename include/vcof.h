@@ -37,6 +37,11 @@ int vcof_abi_version(void);
 #define VCOF_EPI_GATE_ACCUM_BF16 5   /* out_bf16 = bf16(float(out_bf16) + gate[n] * acc): in-place LoRA merge
                                         W += multiplier * alpha/rank * up @ down (utils/lora_utils.py:482-496) */
 
+#define VCOF_EPI_MUL_BF16 6          /* out_bf16 = bf16(float(out_bf16) * bf16(acc + bias)): gated FFN of the text
+                                        encoder, `out` holds gelu(gate(x)) (wan_text_encoder.py:129)             */
+#define VCOF_EPI_ADD_BF16 7          /* out_bf16 = bf16(float(out_bf16) + bf16(acc + bias)): bf16 residual stream
+                                        of the text encoder (wan_text_encoder.py:156-157)                        */
+
 /* D[M,N] = A[M,K] (bf16) x W[N,K]^T (bf16, nn.Linear layout) with fused epilogue; tcgen05 +
  * TMEM + TMA.  Replaces nn.Linear q/k/v/o, ffn.0/ffn.2, text_embedding, head.head and the
  * patch-embedding Conv3d-as-GEMM: wan_transformer3d.py:264-267, 284-290, 303-304, 457-459,
@@ -164,6 +169,29 @@ int vcof_cl_to_nchw(const void* x, long long ldx, void* y, int C, long long thw,
  * GEMM (raw fp32 scores) -> this -> GEMM (wan_vae.py:244-266). */
 int vcof_softmax_rows(const float* s, long long lds, void* p, long long ldp, int rows, int n, float scale,
                       void* stream);
+
+/* ---- umT5 text encoder (bias-free Linears run on vcof_gemm_bf16) -------------------- */
+
+/* out_bf16[i, :] = table_bf16[ids[i], :] for i < n; ids are int64 DEVICE values in [0, vocab) (an id outside the range
+ * yields a zero row, never a wild read; the host wrapper validates ids).  nn.Embedding lookup,
+ * wan_text_encoder.py:269-270, 285. */
+int vcof_embed_rows(const long long* ids, const void* table, long long ldt, long long vocab, void* out, long long ldo,
+                    long long n, int C, void* stream);
+
+/* y = bf16(w * bf16(x * rsqrt(mean(x^2) + eps))) per row of x_bf16[rows, C]; the fp32 factor is not rounded
+ * (T5LayerNorm, wan_text_encoder.py:45-57 — differs from WanRMSNorm, which rounds it). */
+int vcof_t5_rmsnorm(const void* x, long long ldx, const void* weight, void* y, long long ldy, long long rows, int C,
+                    float eps, void* stream);
+
+/* T5 self-attention for B samples of L <= 512 tokens: q/k/v/out are bf16 [B*L, heads*head_dim] (sample-major rows,
+ * heads interleaved along the row as .view(b, -1, n, c)); scores = q.k (NO 1/sqrt(d)) + bias_rel[h][(j - i) + L - 1]
+ * with bias_rel fp32 [heads, bias_ld >= 2L-1] (the position bias depends on key - query only); a key with
+ * key_mask[b*L + j] == 0 gets finfo(bf16).min in place of its bias (masked_fill_, :94-98; key_mask int32 or NULL);
+ * fp32 softmax, probabilities rounded to bf16, fp32 P.V, bf16 store.  head_dim in {16, 32, 64, 128}.
+ * Replaces T5Attention.forward + T5RelativeEmbedding.forward, wan_text_encoder.py:76-112, 207-222. */
+int vcof_t5_attn(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
+                 long long ldo, const float* bias_rel, int bias_ld, const int* key_mask, int B, int L, int heads,
+                 int head_dim, void* stream);
 
 /* ---- diagnostics ---------------------------------------------------------------------- */
 /* One 128x128x64 tcgen05 tile with hand-swizzled operands (no TMA): d_f32[128,128] =

@@ -128,7 +128,7 @@ def t5_attention(p, pre, x, mask, bias, cfg, emu=False):
     s = torch.einsum("inc,jnc->nij", q, k) + ab
     a = _rb(torch.softmax(s.float(), dim=-1), emu)
     o = _rb(torch.einsum("nij,jnc->inc", a, v).reshape(-1, n * c), emu)
-    return lin(o, p[pre + "o.weight"].float())
+    return _rb(lin(o, p[pre + "o.weight"].float()), emu)
 
 
 def t5_forward(p, cfg, ids, mask=None, emulate_bf16=False):
@@ -152,6 +152,6 @@ def t5_forward(p, cfg, ids, mask=None, emulate_bf16=False):
             h = t5_layer_norm(x, p[pre + "norm2.weight"], cfg.eps, emu)
             g = _rb(gelu_tanh(_rb(lin(h, p[pre + "ffn.gate.0.weight"].float()), emu)), emu)
             u = _rb(_rb(lin(h, p[pre + "ffn.fc1.weight"].float()), emu) * g, emu)
-            x = _rb(x + lin(u, p[pre + "ffn.fc2.weight"].float()), emu)
+            x = _rb(x + _rb(lin(u, p[pre + "ffn.fc2.weight"].float()), emu), emu)
         outs.append(t5_layer_norm(x, p["norm.weight"], cfg.eps, emu))
     return torch.stack(outs)

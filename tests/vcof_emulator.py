@@ -13,10 +13,16 @@ def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
     if epilogue == "gate_accum":          # in place: out = bf16(float(out) + gate[n] * acc)
         out.copy_((out.float() + gate.float() * acc).to(torch.bfloat16))
         return out
+    if epilogue in ("mul", "add"):        # in place on bf16 `out`, the Linear output rounded to bf16 first
+        r = acc.to(torch.bfloat16).float()
+        out.copy_((out.float() * r if epilogue == "mul" else out.float() + r).to(torch.bfloat16))
+        return out
     if epilogue == "raw_f32":
         res = acc
     elif epilogue == "bias":
         res = acc.to(torch.bfloat16)
+    elif epilogue == "bias_gelu":
+        res = torch.nn.functional.gelu(acc.to(torch.bfloat16).float(), approximate="tanh").to(torch.bfloat16)
     else:
         raise NotImplementedError(epilogue)
     if out is not None:
@@ -143,6 +149,48 @@ def cl_to_nchw(x, C, sub=None, mul=None):
 
 def softmax_rows(s, scale, out=None):
     return torch.softmax(s.float() * scale, dim=-1).to(torch.bfloat16)
+
+
+# ---- umT5 text encoder entry points (include/vcof.h: vcof_embed_rows, vcof_t5_rmsnorm, vcof_t5_attn) ----------------
+def embed_rows(ids, table, out=None):
+    res = table[ids]
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res.clone()
+
+
+def t5_rmsnorm(x, weight, eps=1e-6, out=None):
+    xf = x.float()
+    y = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(torch.bfloat16).float()
+    res = (weight.float() * y).to(torch.bfloat16)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def t5_attention(q, k, v, bias_rel, B, L, heads, key_mask=None, out=None):
+    d = q.shape[1] // heads
+    qf, kf, vf = (t.float().view(B, L, heads, d) for t in (q, k, v))
+    idx = (torch.arange(L)[None, :] - torch.arange(L)[:, None]) + L - 1              # (key - query) + L - 1
+    s = torch.einsum("binc,bjnc->bnij", qf, kf)
+    bias = bias_rel[:, idx].unsqueeze(0).expand(B, -1, -1, -1).clone()               # [B, heads, L, L]
+    if key_mask is not None:
+        bias.masked_fill_((key_mask == 0).view(B, 1, 1, L), torch.finfo(torch.bfloat16).min)
+    p = torch.softmax(s + bias, dim=-1).to(torch.bfloat16).float()
+    res = torch.einsum("bnij,bjnc->binc", p, vf).reshape(B * L, heads * d).to(torch.bfloat16)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def install_t5(monkeypatch):
+    from videocof_b200 import ops, text_encoder
+    for name in ("gemm", "embed_rows", "t5_rmsnorm", "t5_attention"):
+        monkeypatch.setattr(ops, name, globals()[name])
+    monkeypatch.setattr(text_encoder.WanT5EncoderModel, "_check", lambda self: None)
 
 
 def install(monkeypatch):

@@ -169,6 +169,34 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& p, uint32_t t
           for (int j = 0; j < 32; ++j)
             if (n0 + j < p.N) o[j] = __float2bfloat16_rn(__bfloat162float(o[j]) + p.gate[n0 + j] * v[j]);
         }
+      } else if (EPI == VCOF_EPI_MUL_BF16 || EPI == VCOF_EPI_ADD_BF16) {
+        // bf16 read-modify-write with the Linear output rounded to bf16 first, as the reference's eager bf16 ops do:
+        // MUL: u = fc1(x) * gelu(gate(x)) with `out` holding the gate branch (wan_text_encoder.py:129);
+        // ADD: x = x + o(attn) / x + fc2(u) on the bf16 residual stream (wan_text_encoder.py:156-157)
+        bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + n0;
+        if (full_chunk) {
+          uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 w = o4[q];
+            const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+            uint32_t r[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(w2[e]);
+              const float a0 = bf16_round(v[q * 8 + e * 2]), a1 = bf16_round(v[q * 8 + e * 2 + 1]);
+              r[e] = (EPI == VCOF_EPI_MUL_BF16) ? pack_bf16x2(f.x * a0, f.y * a1) : pack_bf16x2(f.x + a0, f.y + a1);
+            }
+            o4[q] = make_uint4(r[0], r[1], r[2], r[3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) {
+              const float f = __bfloat162float(o[j]), a = bf16_round(v[j]);
+              o[j] = __float2bfloat16_rn((EPI == VCOF_EPI_MUL_BF16) ? f * a : f + a);
+            }
+        }
       } else if (EPI == VCOF_EPI_RAW_F32) {  // out = acc + bias, unrounded (attention scores)
         float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0;
         if (full_chunk) {
@@ -542,6 +570,8 @@ static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
     case VCOF_EPI_RAW_F32: return launch_gemm<BN, VCOF_EPI_RAW_F32>(tmA, tmB, args, stream);
     case VCOF_EPI_GATE_ACCUM_BF16:
       return launch_gemm<BN, VCOF_EPI_GATE_ACCUM_BF16>(tmA, tmB, args, stream);
+    case VCOF_EPI_MUL_BF16: return launch_gemm<BN, VCOF_EPI_MUL_BF16>(tmA, tmB, args, stream);
+    case VCOF_EPI_ADD_BF16: return launch_gemm<BN, VCOF_EPI_ADD_BF16>(tmA, tmB, args, stream);
   }
   set_last_error("vcof_gemm_bf16: unknown epilogue %d", epi);
   return -1;

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-EPI = {"bias": 0, "bias_gelu": 1, "bias_gate_res": 2, "bias_f32": 3, "raw_f32": 4, "gate_accum": 5}
+EPI = {"bias": 0, "bias_gelu": 1, "bias_gate_res": 2, "bias_f32": 3, "raw_f32": 4, "gate_accum": 5, "mul": 6, "add": 7}
 
 # kernel launches since the last reset (bench.py reports it as gpu_launches)
 _launches = 0
@@ -87,7 +87,8 @@ def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
 
     epilogue: "bias" -> bf16 [M,N]; "bias_gelu" -> bf16 gelu_tanh; "bias_f32" -> fp32 (value
     rounded through bf16); "bias_gate_res" -> `out` (fp32 [M,N], required) += gate * bf16(.);
-    "gate_accum" -> `out` (bf16 [M,N], required) = bf16(float(out) + gate[n] * (a @ w.T)) (LoRA merge)
+    "gate_accum" -> `out` (bf16 [M,N], required) = bf16(float(out) + gate[n] * (a @ w.T)) (LoRA merge);
+    "mul" / "add" -> `out` (bf16 [M,N], required) = bf16(float(out) * or + bf16(a @ w.T + bias)) (text encoder)
     """
     _chk(a, torch.bfloat16, "gemm.a", 2)
     _chk(w, torch.bfloat16, "gemm.w", 2)
@@ -111,6 +112,10 @@ def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
     elif epi == 5:
         if out is None or gate is None or bias is not None:
             raise _lib.VcofError("gemm: gate_accum updates `out` in place with a per-column gate and no bias")
+        _chk(out, torch.bfloat16, "gemm.out", 2)
+    elif epi in (6, 7):
+        if out is None:
+            raise _lib.VcofError(f"gemm: {epilogue} updates the bf16 tensor passed as `out` in place")
         _chk(out, torch.bfloat16, "gemm.out", 2)
     else:
         if out is None:
@@ -363,4 +368,61 @@ def softmax_rows(s, scale, out=None):
         out = torch.empty((rows, (n + 7) // 8 * 8), dtype=torch.bfloat16, device=s.device)[:, :n]
     _call("vcof_softmax_rows", s.data_ptr(), s.stride(0), out.data_ptr(), out.stride(0), rows, n, float(scale),
           _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# umT5 text encoder ops (bf16 activations [tokens, C])
+# ------------------------------------------------------------------------------------------------
+def embed_rows(ids, table, out=None):
+    """table[ids] for int64 ids [n] on the device; table bf16 [vocab, C]."""
+    _chk(ids, torch.int64, "embed_rows.ids", 1)
+    _chk(table, torch.bfloat16, "embed_rows.table", 2)
+    if not ids.is_contiguous():
+        raise _lib.VcofError("embed_rows.ids must be contiguous")
+    n, (vocab, C) = ids.numel(), table.shape
+    if out is None:
+        out = torch.empty((n, C), dtype=torch.bfloat16, device=table.device)
+    _chk(out, torch.bfloat16, "embed_rows.out", 2)
+    _call("vcof_embed_rows", ids.data_ptr(), table.data_ptr(), table.stride(0), vocab, out.data_ptr(), out.stride(0),
+          n, C, _stream())
+    return out
+
+
+def t5_rmsnorm(x, weight, eps=1e-6, out=None):
+    """T5LayerNorm: bf16(w * bf16(x * rsqrt(mean(x^2) + eps))); x bf16 [rows, C], weight bf16 [C]."""
+    _chk(x, torch.bfloat16, "t5_rmsnorm.x", 2)
+    _chk(weight, torch.bfloat16, "t5_rmsnorm.weight", 1)
+    rows, C = x.shape
+    if weight.numel() != C:
+        raise _lib.VcofError(f"t5_rmsnorm: weight has {weight.numel()} entries for C={C}")
+    if out is None:
+        out = torch.empty((rows, C), dtype=torch.bfloat16, device=x.device)
+    _chk(out, torch.bfloat16, "t5_rmsnorm.out", 2)
+    _call("vcof_t5_rmsnorm", x.data_ptr(), x.stride(0), weight.data_ptr(), out.data_ptr(), out.stride(0), rows, C,
+          float(eps), _stream())
+    return out
+
+
+def t5_attention(q, k, v, bias_rel, B, L, heads, key_mask=None, out=None):
+    """softmax(q k^T + bias) v per head, unscaled.  q/k/v bf16 [B*L, heads*d]; bias_rel fp32 [heads, 2L-1] indexed by
+    (key - query) + L - 1; key_mask int32 [B, L] (0 = masked) or None."""
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _chk(t, torch.bfloat16, "t5_attention." + n, 2)
+        if t.shape[0] != B * L:
+            raise _lib.VcofError(f"t5_attention.{n}: {t.shape[0]} rows for B={B}, L={L}")
+    _chk(bias_rel, torch.float32, "t5_attention.bias_rel", 2)
+    if bias_rel.shape[0] != heads or bias_rel.shape[1] < 2 * L - 1:
+        raise _lib.VcofError(f"t5_attention.bias_rel: shape {tuple(bias_rel.shape)} for heads={heads}, L={L}")
+    if key_mask is not None:
+        _chk(key_mask, torch.int32, "t5_attention.key_mask", 2)
+        if tuple(key_mask.shape) != (B, L) or not key_mask.is_contiguous():
+            raise _lib.VcofError(f"t5_attention.key_mask: need a contiguous [{B}, {L}] tensor")
+    C = q.shape[1]
+    if out is None:
+        out = torch.empty((B * L, C), dtype=torch.bfloat16, device=q.device)
+    _chk(out, torch.bfloat16, "t5_attention.out", 2)
+    _call("vcof_t5_attn", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+          out.data_ptr(), out.stride(0), bias_rel.data_ptr(), bias_rel.stride(0), _p(key_mask), B, L, heads,
+          C // heads, _stream(), key=f"t5_attn B={B} L={L} heads={heads}")
     return out
