@@ -42,6 +42,11 @@ int vcof_abi_version(void);
 #define VCOF_EPI_ADD_BF16 7          /* out_bf16 = bf16(float(out_bf16) + bf16(acc + bias)): bf16 residual stream
                                         of the text encoder (wan_text_encoder.py:156-157)                        */
 
+/* Optional flag OR-ed into `epilogue`: tile the output 128 columns wide instead of 256.  For skinny problems (the text
+ * encoder's M = 512 tokens) whose 256-wide tiling would occupy less than the machine or spill a few tiles into a second
+ * wave; the caller decides (videocof_b200/ops.py: gemm(..., narrow=True)).  Results are identical. */
+#define VCOF_GEMM_TILE128 0x100
+
 /* D[M,N] = A[M,K] (bf16) x W[N,K]^T (bf16, nn.Linear layout) with fused epilogue; tcgen05 +
  * TMEM + TMA.  Replaces nn.Linear q/k/v/o, ffn.0/ffn.2, text_embedding, head.head and the
  * patch-embedding Conv3d-as-GEMM: wan_transformer3d.py:264-267, 284-290, 303-304, 457-459,

@@ -98,11 +98,11 @@ static void case_embed(int n, int vocab, int C) {
   cudaFree(dt); cudaFree(di); cudaFree(dy);
 }
 
-static void case_gemm(int M, int N, int K, int epi) {
+static void case_gemm(int M, int N, int K, int epi, int flags = 0) {
   auto a = rand_bf16((size_t)M * K, 1.0), w = rand_bf16((size_t)N * K, 1.0 / sqrt((double)K));
   auto o0 = rand_bf16((size_t)M * N, 1.0);
   bf16 *da = to_dev(a), *dw = to_dev(w), *dout = to_dev(o0);
-  const int rc = vcof_gemm_bf16(da, K, dw, K, nullptr, nullptr, dout, N, M, N, K, epi, nullptr);
+  const int rc = vcof_gemm_bf16(da, K, dw, K, nullptr, nullptr, dout, N, M, N, K, epi | flags, nullptr);
   std::vector<double> ref((size_t)M * N);
   std::vector<float> af((size_t)M * K), wf((size_t)N * K);
   for (size_t i = 0; i < af.size(); ++i) af[i] = __bfloat162float(a[i]);
@@ -118,7 +118,7 @@ static void case_gemm(int M, int N, int K, int epi) {
                                    ? 0.5 * lin * (1.0 + tanh(0.7978845608028654 * (lin + 0.044715 * lin * lin * lin)))
                                    : acc;
     }
-  char shape[64]; snprintf(shape, sizeof shape, "M=%d N=%d K=%d", M, N, K);
+  char shape[64]; snprintf(shape, sizeof shape, "M=%d N=%d K=%d%s", M, N, K, flags ? " tile128" : "");
   report(epi == VCOF_EPI_MUL_BF16 ? "gemm_mul" : epi == VCOF_EPI_ADD_BF16 ? "gemm_add"
          : epi == VCOF_EPI_BIAS_GELU_BF16 ? "gemm_gelu_nobias" : "gemm_nobias",
          shape, to_host(dout, (size_t)M * N), ref, 4e-3, rc);
@@ -166,7 +166,127 @@ static void case_attn(int B, int L, int heads, int d, const int* lens) {
   cudaFree(dq); cudaFree(dk); cudaFree(dv); cudaFree(dout); cudaFree(db); cudaFree(dm);
 }
 
+// ---- --bench: the kernel sequence of one umT5-XXL encode (24 layers, dim 4096, 64 heads x 64, ffn 10240) on `n`
+// tokens, exactly what videocof_b200/text_encoder.py launches, timed with CUDA events on the launching stream.
+// Weights are random and come in 4 distinct layer sets (1.5 GB, cycled) so no weight is served from L2 twice.
+struct LayerW { bf16 *q, *k, *v, *o, *gate, *fc1, *fc2, *n1, *n2; };
+static bf16* dev_random(size_t n, const bf16* seed_dev, size_t seed_n) {
+  bf16* d = nullptr;
+  if (cudaMalloc(&d, n * 2) != cudaSuccess) { fprintf(stderr, "cudaMalloc failed\n"); exit(2); }
+  for (size_t off = 0; off < n; off += seed_n)
+    cudaMemcpy(d + off, seed_dev, (n - off < seed_n ? n - off : seed_n) * 2, cudaMemcpyDeviceToDevice);
+  return d;
+}
+static int bench(const char* out_path, int n, int narrow) {
+  const int D = 4096, F = 10240, H = 64, LAYERS = 24, SETS = 4, L = n;
+  const size_t seed_n = (size_t)8 << 20;
+  auto seed = rand_bf16(seed_n, 1.0 / 64.0);
+  bf16* dseed = to_dev(seed);
+  LayerW w[SETS];
+  auto ones = std::vector<bf16>(D, __float2bfloat16_rn(1.0f));
+  for (auto& l : w) {
+    l.q = dev_random((size_t)D * D, dseed, seed_n); l.k = dev_random((size_t)D * D, dseed + 4099, seed_n - 4099);
+    l.v = dev_random((size_t)D * D, dseed + 131, seed_n - 131); l.o = dev_random((size_t)D * D, dseed + 977, seed_n - 977);
+    l.gate = dev_random((size_t)F * D, dseed + 17, seed_n - 17); l.fc1 = dev_random((size_t)F * D, dseed + 3001, seed_n - 3001);
+    l.fc2 = dev_random((size_t)D * F, dseed + 555, seed_n - 555);
+    l.n1 = to_dev(ones); l.n2 = to_dev(ones);
+  }
+  auto tab = rand_bf16((size_t)1024 * D, 1.0);
+  bf16* dtab = to_dev(tab);
+  std::vector<long long> ids(n);
+  for (auto& i : ids) i = (long long)(urand() * 1024) % 1024;
+  long long* dids = to_dev(ids);
+  std::vector<float> bias((size_t)H * (2 * L - 1));
+  for (auto& b : bias) b = (float)nrand();
+  float* dbias = to_dev(bias);
+  bf16 *x, *h, *q, *k, *v, *a, *g, *y;
+  cudaMalloc(&x, (size_t)n * D * 2); cudaMalloc(&h, (size_t)n * D * 2); cudaMalloc(&q, (size_t)n * D * 2);
+  cudaMalloc(&k, (size_t)n * D * 2); cudaMalloc(&v, (size_t)n * D * 2); cudaMalloc(&a, (size_t)n * D * 2);
+  cudaMalloc(&g, (size_t)n * F * 2); cudaMalloc(&y, (size_t)n * D * 2);
+  const int fl = narrow ? VCOF_GEMM_TILE128 : 0;
+  enum { K_NORM, K_QKV, K_ATTN, K_O, K_GATE, K_FC1, K_FC2, K_EMBED, K_N };
+  const char* names[K_N] = {"t5_rmsnorm", "gemm_qkv", "t5_attn", "gemm_o_add", "gemm_gate_gelu", "gemm_fc1_mul",
+                            "gemm_fc2_add", "embed_rows"};
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_kind;
+  int rc = 0, launches = 0;
+  auto pass = [&](bool per_kernel) {
+    auto mark = [&](int kind) {
+      if (!per_kernel) return;
+      cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, 0); ev.push_back(e); ev_kind.push_back(kind);
+    };
+    launches = 0;
+    mark(-1);
+    rc |= vcof_embed_rows(dids, dtab, D, 1024, x, D, n, D, nullptr); ++launches; mark(K_EMBED);
+    for (int l = 0; l < LAYERS; ++l) {
+      const LayerW& W = w[l % SETS];
+      rc |= vcof_t5_rmsnorm(x, D, W.n1, h, D, n, D, 1e-6f, nullptr); mark(K_NORM);
+      rc |= vcof_gemm_bf16(h, D, W.q, D, nullptr, nullptr, q, D, n, D, D, VCOF_EPI_BIAS_BF16 | fl, nullptr);
+      rc |= vcof_gemm_bf16(h, D, W.k, D, nullptr, nullptr, k, D, n, D, D, VCOF_EPI_BIAS_BF16 | fl, nullptr);
+      rc |= vcof_gemm_bf16(h, D, W.v, D, nullptr, nullptr, v, D, n, D, D, VCOF_EPI_BIAS_BF16 | fl, nullptr); mark(K_QKV);
+      rc |= vcof_t5_attn(q, D, k, D, v, D, a, D, dbias, 2 * L - 1, nullptr, 1, L, H, D / H, nullptr); mark(K_ATTN);
+      rc |= vcof_gemm_bf16(a, D, W.o, D, nullptr, nullptr, x, D, n, D, D, VCOF_EPI_ADD_BF16 | fl, nullptr); mark(K_O);
+      rc |= vcof_t5_rmsnorm(x, D, W.n2, h, D, n, D, 1e-6f, nullptr); mark(K_NORM);
+      rc |= vcof_gemm_bf16(h, D, W.gate, D, nullptr, nullptr, g, F, n, F, D, VCOF_EPI_BIAS_GELU_BF16 | fl, nullptr); mark(K_GATE);
+      rc |= vcof_gemm_bf16(h, D, W.fc1, D, nullptr, nullptr, g, F, n, F, D, VCOF_EPI_MUL_BF16 | fl, nullptr); mark(K_FC1);
+      rc |= vcof_gemm_bf16(g, F, W.fc2, F, nullptr, nullptr, x, D, n, D, F, VCOF_EPI_ADD_BF16 | fl, nullptr); mark(K_FC2);
+      launches += 10;
+    }
+    rc |= vcof_t5_rmsnorm(x, D, w[0].n1, y, D, n, D, 1e-6f, nullptr); ++launches; mark(K_NORM);
+  };
+  for (int i = 0; i < 3; ++i) pass(false);
+  if (rc || cudaDeviceSynchronize() != cudaSuccess) {
+    printf("{\"bench\": \"failed\", \"rc\": %d, \"error\": \"%s\"}\n", rc, vcof_last_error());
+    return 1;
+  }
+  const int REPS = 10;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, 0);
+  for (int i = 0; i < REPS; ++i) pass(false);
+  cudaEventRecord(e1, 0);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms /= REPS;
+  pass(true);
+  cudaDeviceSynchronize();
+  double per[K_N] = {0};
+  for (size_t i = 1; i < ev.size(); ++i) {
+    float t = 0;
+    cudaEventElapsedTime(&t, ev[i - 1], ev[i]);
+    per[ev_kind[i]] += t;
+  }
+  std::vector<bf16> yh = to_host(y, (size_t)n * D);
+  bool nan = false;
+  for (auto& e : yh) { const float f = __bfloat162float(e); if (f != f) nan = true; }
+  const double gemm_flops = (double)LAYERS * 2.0 * n * (4.0 * D * D + 3.0 * D * F);
+  const double attn_flops = (double)LAYERS * 4.0 * n * (double)n * D;
+  const double weight_bytes = (double)LAYERS * 2.0 * (4.0 * D * D + 3.0 * D * F);
+  char line[1024];
+  int o = snprintf(line, sizeof line, "{\"bench\": \"umt5_xxl_encode\", \"tokens\": %d, \"layers\": %d, \"tile128\": %d, "
+                   "\"ms_per_encode\": %.4f, \"launches\": %d, \"gemm_tflop\": %.4f, \"attn_tflop\": %.4f, "
+                   "\"achieved_tflops\": %.1f, \"weight_gb\": %.3f, \"weight_stream_gbs\": %.1f, \"nan\": %s, "
+                   "\"per_kernel_ms\": {", n, LAYERS, narrow, ms, launches, gemm_flops / 1e12, attn_flops / 1e12,
+                   (gemm_flops + attn_flops) / (ms * 1e-3) / 1e12, weight_bytes / 1e9, weight_bytes / (ms * 1e-3) / 1e9,
+                   nan ? "true" : "false");
+  for (int i = 0; i < K_N; ++i)
+    o += snprintf(line + o, sizeof line - o, "%s\"%s\": %.4f", i ? ", " : "", names[i], per[i]);
+  snprintf(line + o, sizeof line - o, "}}");
+  puts(line);
+  if (out_path) { FILE* f = fopen(out_path, "a"); if (f) { fputs(line, f); fputc('\n', f); fclose(f); } }
+  return nan ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && strcmp(argv[1], "--bench") == 0) {
+    const char* out = argc > 2 ? argv[2] : nullptr;
+    int bad = 0;
+    bad |= bench(out, 512, 1);
+    bad |= bench(out, 512, 0);
+    bad |= bench(out, 128, 1);
+    return bad;
+  }
   if (argc > 1) g_out = fopen(argv[1], "w");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { puts("{\"error\": \"no CUDA device\"}"); return 3; }
@@ -183,13 +303,19 @@ int main(int argc, char** argv) {
   case_attn(1, 300, 2, 128, nullptr);
   case_attn(2, 512, 4, 64, l512);
   case_attn(1, 512, 8, 64, nullptr);
-  const int shapes[4][3] = {{192, 256, 256}, {200, 104, 64}, {333, 1024, 512}, {512, 4096, 1024}};
+  const int shapes[4][3] = {{192, 256, 256}, {200, 104, 64}, {333, 1024, 512}, {512, 4096, 512}};
   for (auto& sh : shapes) {
     case_gemm(sh[0], sh[1], sh[2], VCOF_EPI_MUL_BF16);
     case_gemm(sh[0], sh[1], sh[2], VCOF_EPI_ADD_BF16);
   }
   case_gemm(192, 512, 256, VCOF_EPI_BIAS_GELU_BF16);
   case_gemm(192, 256, 512, VCOF_EPI_BIAS_BF16);
+  // 128-wide tiles over several tile columns (VCOF_GEMM_TILE128: what the text encoder asks for at M = 512)
+  case_gemm(512, 4096, 256, VCOF_EPI_MUL_BF16, VCOF_GEMM_TILE128);
+  case_gemm(512, 4096, 256, VCOF_EPI_ADD_BF16, VCOF_GEMM_TILE128);
+  case_gemm(333, 1000, 512, VCOF_EPI_BIAS_GELU_BF16, VCOF_GEMM_TILE128);
+  case_gemm(77, 2560, 256, VCOF_EPI_BIAS_BF16, VCOF_GEMM_TILE128);
+  case_gemm(640, 304, 192, VCOF_EPI_ADD_BF16, VCOF_GEMM_TILE128);
   printf("{\"failed\": %d}\n", g_fail);
   if (g_out) { fprintf(g_out, "{\"failed\": %d}\n", g_fail); fclose(g_out); }
   return g_fail ? 1 : 0;

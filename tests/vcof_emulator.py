@@ -6,7 +6,7 @@ parity views, first-frame rules, frame interleave) is checked against the refere
 import torch
 
 
-def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
+def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None, narrow=False):
     acc = a.float() @ w.float().t()
     if bias is not None:
         acc = acc + bias.float()

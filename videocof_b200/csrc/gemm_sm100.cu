@@ -585,6 +585,8 @@ extern "C" int vcof_gemm_bf16(const void* a, long long lda, const void* w, long 
                               const void* bias, const float* gate, void* out, long long ldo, int M,
                               int N, int K, int epilogue, void* stream) {
   VCOF_REQUIRE(M > 0 && N > 0 && K > 0, "vcof_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  const bool narrow = (epilogue & VCOF_GEMM_TILE128) != 0;
+  epilogue &= ~VCOF_GEMM_TILE128;
   VCOF_REQUIRE(lda % 8 == 0 && ldw % 8 == 0,
                "vcof_gemm_bf16: lda/ldw must be multiples of 8 (16-byte TMA rows)");
   const bool f32_out = (epilogue == VCOF_EPI_BIAS_GATE_RES_F32 || epilogue == VCOF_EPI_BIAS_F32 ||
@@ -598,7 +600,8 @@ extern "C" int vcof_gemm_bf16(const void* a, long long lda, const void* w, long 
                "vcof_gemm_bf16: gate not 16B aligned");
   VCOF_REQUIRE(epilogue != VCOF_EPI_GATE_ACCUM_BF16 || (gate != nullptr && bias == nullptr),
                "vcof_gemm_bf16: the accumulate epilogue needs a gate vector and takes no bias");
-  const int BN = (N > 128) ? 256 : (N > 64 ? 128 : 64);
+  // VCOF_GEMM_TILE128: the caller asks for 128-wide tiles (skinny problems whose 256-wide tiling would leave SMs idle)
+  const int BN = (N > 128) ? (narrow ? 128 : 256) : (N > 64 ? 128 : 64);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d_bf16(&tmA, a, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kBM);
   if (rc) return rc;
@@ -623,7 +626,7 @@ extern "C" int vcof_gemm_bf16(const void* a, long long lda, const void* w, long 
     const char* e = getenv("VCOF_GEMM_2CTA");
     return e != nullptr && e[0] == '1';
   }();
-  if (pair_mode && N >= 256 && M >= 256 && epilogue <= VCOF_EPI_BIAS_GATE_RES_F32) {
+  if (pair_mode && !narrow && N >= 256 && M >= 256 && epilogue <= VCOF_EPI_BIAS_GATE_RES_F32) {
     // experimental CTA-pair kernel: B box is this CTA's 128-row half of the 256-row tile
     rc = make_tmap_2d_bf16(&tmB, w, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, kBK, 128);
     if (rc) return rc;

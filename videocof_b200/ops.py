@@ -82,13 +82,22 @@ def _chk(t, dtype, name, dims=None):
     return t
 
 
-def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
+def narrow_tiles_pay(M, N, sms=148):
+    """True when 128-wide GEMM tiles finish sooner than 256-wide ones: cost = waves over the SMs x tile width.  Only
+    problems of at most two 256-wide waves qualify, so large GEMMs never change shape."""
+    num_m = (M + 127) // 128
+    t256, t128 = num_m * ((N + 255) // 256), num_m * ((N + 127) // 128)
+    return N > 128 and t256 <= 2 * sms and -(-t128 // sms) * 128 < -(-t256 // sms) * 256
+
+
+def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None, narrow=False):
     """out = epilogue(a @ w.T + bias).  a [M,K] bf16, w [N,K] bf16 (nn.Linear layout).
 
     epilogue: "bias" -> bf16 [M,N]; "bias_gelu" -> bf16 gelu_tanh; "bias_f32" -> fp32 (value
     rounded through bf16); "bias_gate_res" -> `out` (fp32 [M,N], required) += gate * bf16(.);
     "gate_accum" -> `out` (bf16 [M,N], required) = bf16(float(out) + gate[n] * (a @ w.T)) (LoRA merge);
-    "mul" / "add" -> `out` (bf16 [M,N], required) = bf16(float(out) * or + bf16(a @ w.T + bias)) (text encoder)
+    "mul" / "add" -> `out` (bf16 [M,N], required) = bf16(float(out) * or + bf16(a @ w.T + bias)) (text encoder).
+    narrow: 128-wide output tiles (VCOF_GEMM_TILE128) — same result, better SM occupancy for skinny problems.
     """
     _chk(a, torch.bfloat16, "gemm.a", 2)
     _chk(w, torch.bfloat16, "gemm.w", 2)
@@ -124,7 +133,7 @@ def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None):
     if tuple(out.shape) != (M, N):
         raise _lib.VcofError(f"gemm: out shape {tuple(out.shape)} != {(M, N)}")
     _call("vcof_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _p(bias),
-          _p(gate), out.data_ptr(), out.stride(0), M, N, K, epi, _stream(),
+          _p(gate), out.data_ptr(), out.stride(0), M, N, K, epi | (0x100 if narrow else 0), _stream(),
           key=f"gemm[{epilogue}] M={M} N={N} K={K}")
     return out
 

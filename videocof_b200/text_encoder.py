@@ -127,16 +127,18 @@ class T5SelfAttention(nn.Module):
     def run(self, x, ws, bias_rel, mask, B, L):
         """x bf16 [B*L, dim], updated in place (the bf16 residual stream of the reference's eager path)."""
         at, ff = self.attn, self.ffn
+        n = x.shape[0]                                                        # <= a few 128-row tiles: pick the
+        na, nd, nf = (ops.narrow_tiles_pay(n, w, ws.sms) for w in (self.dim_attn, self.dim, self.dim_ffn))  # tile width
         ops.t5_rmsnorm(x, self.norm1.weight, self.norm1.eps, out=ws.h)
-        ops.gemm(ws.h, at.q.weight, None, "bias", out=ws.q)
-        ops.gemm(ws.h, at.k.weight, None, "bias", out=ws.k)
-        ops.gemm(ws.h, at.v.weight, None, "bias", out=ws.v)
+        ops.gemm(ws.h, at.q.weight, None, "bias", out=ws.q, narrow=na)
+        ops.gemm(ws.h, at.k.weight, None, "bias", out=ws.k, narrow=na)
+        ops.gemm(ws.h, at.v.weight, None, "bias", out=ws.v, narrow=na)
         ops.t5_attention(ws.q, ws.k, ws.v, bias_rel, B, L, self.num_heads, key_mask=mask, out=ws.a)
-        ops.gemm(ws.a, at.o.weight, None, "add", out=x)                       # x = x + o(attn)          (:156)
+        ops.gemm(ws.a, at.o.weight, None, "add", out=x, narrow=nd)            # x = x + o(attn)          (:156)
         ops.t5_rmsnorm(x, self.norm2.weight, self.norm2.eps, out=ws.h)
-        ops.gemm(ws.h, ff.gate[0].weight, None, "bias_gelu", out=ws.g)        # gelu(gate(x))            (:120, :129)
-        ops.gemm(ws.h, ff.fc1.weight, None, "mul", out=ws.g)                  # fc1(x) * gelu(gate(x))   (:129)
-        ops.gemm(ws.g, ff.fc2.weight, None, "add", out=x)                     # x = x + fc2(.)           (:131, :157)
+        ops.gemm(ws.h, ff.gate[0].weight, None, "bias_gelu", out=ws.g, narrow=nf)   # gelu(gate(x))      (:120, :129)
+        ops.gemm(ws.h, ff.fc1.weight, None, "mul", out=ws.g, narrow=nf)       # fc1(x) * gelu(gate(x))   (:129)
+        ops.gemm(ws.g, ff.fc2.weight, None, "add", out=x, narrow=nd)          # x = x + fc2(.)           (:131, :157)
         return x
 
 
@@ -154,6 +156,8 @@ class _Workspace:
             self.v = torch.empty((n, dim_attn), **bf)
             self.a = torch.empty((n, dim_attn), **bf)
             self.g = torch.empty((n, dim_ffn), **bf)
+            self.sms = torch.cuda.get_device_properties(device).multi_processor_count if torch.cuda.is_available() \
+                else 148
             self.key = key
         return self
 

@@ -3,8 +3,7 @@
 Put this repository BEFORE the reference checkout on PYTHONPATH: `videox_fun.models` /
 `videox_fun.pipeline` / `videox_fun.utils.fm_solvers_unipc` / `videox_fun.utils.lora_utils` then resolve
 to the B200-native implementations in `videocof_b200`, while every other sub-module the CLIs import
-(`utils.fp8_optimization`, `utils.utils`, `data.dataset_image_video`,
-`models.wan_text_encoder`, …) still resolves to the UNMODIFIED reference files through the
+(`utils.fp8_optimization`, `utils.utils`, `data.dataset_image_video`, …) still resolves to the UNMODIFIED reference files through the
 extended package search path.  See INTEGRATION.md.
 """
 import os
