@@ -287,15 +287,19 @@ int main(int argc, char** argv) {
     bad |= bench(out, 128, 1);
     return bad;
   }
+  const bool attn_only = argc > 1 && strcmp(argv[1], "--attn") == 0;   // attention cases + one encoder bench
+  if (attn_only) { --argc; ++argv; }
   if (argc > 1) g_out = fopen(argv[1], "w");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { puts("{\"error\": \"no CUDA device\"}"); return 3; }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, 0);
   printf("{\"device\": \"%s\", \"sm\": %d%d, \"abi\": %d}\n", prop.name, prop.major, prop.minor, vcof_abi_version());
-  case_embed(777, 1000, 256);
-  case_rmsnorm(1, 64); case_rmsnorm(77, 4096); case_rmsnorm(1024, 256);
-  const int l2[2] = {96, 1}, l3[3] = {160, 13, 100}, l1[1] = {150}, l512[2] = {512, 77};
+  if (!attn_only) {
+    case_embed(777, 1000, 256);
+    case_rmsnorm(1, 64); case_rmsnorm(77, 4096); case_rmsnorm(1024, 256);
+  }
+  const int l2[2] = {96, 1}, l3[3] = {160, 13, 100}, l1[1] = {150}, l512[2] = {512, 77}, lall[2] = {0, 40};
   case_attn(2, 96, 4, 64, l2);
   case_attn(1, 1, 2, 64, nullptr);
   case_attn(3, 160, 4, 16, l3);
@@ -303,6 +307,14 @@ int main(int argc, char** argv) {
   case_attn(1, 300, 2, 128, nullptr);
   case_attn(2, 512, 4, 64, l512);
   case_attn(1, 512, 8, 64, nullptr);
+  case_attn(2, 77, 3, 64, lall);                 // one sample with every key masked (uniform attention)
+  case_attn(1, 129, 2, 64, nullptr);             // ragged: one row in the last 16-row tile / 64-key block
+  if (attn_only) {
+    printf("{\"failed\": %d}\n", g_fail);
+    if (g_out) { fprintf(g_out, "{\"failed\": %d}\n", g_fail); fclose(g_out); }
+    const int bad = bench(argc > 1 ? argv[1] : nullptr, 512, 1);
+    return (g_fail || bad) ? 1 : 0;
+  }
   const int shapes[4][3] = {{192, 256, 256}, {200, 104, 64}, {333, 1024, 512}, {512, 4096, 512}};
   for (auto& sh : shapes) {
     case_gemm(sh[0], sh[1], sh[2], VCOF_EPI_MUL_BF16);

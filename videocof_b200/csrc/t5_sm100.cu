@@ -2,12 +2,14 @@
 // T5LayerNorm and the 64-head x 64-wide relative-position-bias attention of umT5
 // (videox_fun/models/wan_text_encoder.py:45-57, 60-112, 199-247, 281-283).
 //
-// The encoder runs once per prompt on <= 512 tokens: ~5 TFLOP of bias-free Linears (the tcgen05 GEMM with its
-// bf16 multiply / add epilogues) and ~0.1 TFLOP of attention.  The attention is therefore a plain CUDA-core kernel:
-// one CTA per (row block, head, sample) stages that head's K and V (<= 2 x 64 KB) in shared memory once, each warp
-// owns query rows, lanes own keys for the scores and output channels for P·V.  The position bias depends on
-// (key - query) only, so it arrives as a [heads, 2L-1] table instead of the reference's [heads, L, L] tensor.
+// The encoder runs once per prompt on <= 512 tokens: ~4.7 TFLOP of bias-free Linears (the tcgen05 GEMM with its
+// bf16 multiply / add epilogues) and ~0.1 TFLOP of attention over 64-wide heads.  Two attention kernels share one
+// contract: a warp-level tensor-core kernel (mma.sync, the default: 83 us per layer at 512 tokens on a B200) and the
+// first CUDA-core kernel (VCOF_T5_ATTN=simple, 394 us per layer), kept as the independently written cross-check.
+// The position bias depends on (key - query) only, so it arrives as a [heads, 2L-1] table instead of the reference's
+// [heads, L, L] tensor.
 #include <math.h>
+#include <stdlib.h>
 
 #include "vcof_common.cuh"
 #include "../../include/vcof.h"
@@ -92,6 +94,8 @@ constexpr int kT5MaxL = 512;
 constexpr int kT5KeysPerLane = kT5MaxL / 32;
 // torch.finfo(torch.bfloat16).min: what masked_fill_ writes over the bias of a masked key (wan_text_encoder.py:98)
 #define VCOF_BF16_MIN (-3.3895313892515355e38f)
+// which attention kernel vcof_t5_attn runs when VCOF_T5_ATTN is unset (1: mma.sync, 0: CUDA cores)
+#define VCOF_T5_ATTN_DEFAULT_MMA 1
 
 struct T5AttnSmem {
   int k_off, v_off, p_off, q_off, bias_off, mask_off, total;
@@ -231,6 +235,215 @@ static int launch_t5_attn(const void* q, long long ldq, const void* k, long long
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// the same attention on the warp-level tensor-core path (mma.sync m16n8k16, bf16 x bf16 -> fp32)
+// ---------------------------------------------------------------------------
+// 64-wide heads over <= 512 keys are too small for the tcgen05 pipeline of attn_sm100.cu (128-row tiles, 128-wide
+// heads) but far too much arithmetic for CUDA cores (measured 0.39 ms per layer, 57 % of an encode,
+// profiles/r1_gpurun38_bench_t5_native.jsonl).  A warp owns 16 query rows; K sits in shared memory row-major (it is
+// already the "col" B operand of Q.K^T), V transposed (the "col" B operand of P.V).  Two passes over the keys instead
+// of an online rescale: pass 1 finds each row's max and sum, pass 2 recomputes the scores (tensor-core time is
+// free here) and feeds P = bf16(exp(s - max) / sum) — the reference's rounding point (:103) — straight from the
+// accumulator registers into the P.V MMA (the C fragment of two adjacent 8-key tiles is the A fragment of one
+// 16-key step).
+constexpr int kT5MmaWarps = 8;
+constexpr int kT5MmaThreads = kT5MmaWarps * 32;
+constexpr int kT5MmaRows = kT5MmaWarps * 16;
+
+struct T5MmaSmem {
+  int k_off, v_off, bias_off, mask_off, total, Lp;
+};
+
+__host__ __device__ inline T5MmaSmem t5_mma_smem(int L, int D) {
+  T5MmaSmem s;
+  s.Lp = (L + 63) & ~63;
+  int off = 0;
+  s.k_off = off;    off += s.Lp * (D + 8) * 2;      // K[key][D + 8]: pitch = 4 words mod 32 -> conflict-free fragments
+  s.v_off = off;    off += D * (s.Lp + 8) * 2;      // V^T[d][Lp + 8]: same property (Lp % 64 == 0)
+  s.bias_off = off; off += (2 * L - 1) * 4;
+  off = (off + 3) & ~3;
+  s.mask_off = off; off += s.Lp;
+  s.total = (off + 15) & ~15;
+  return s;
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int D>
+__global__ void __launch_bounds__(kT5MmaThreads, 1)
+t5_attn_mma_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ k, long long ldk,
+                   const bf16* __restrict__ v, long long ldv, bf16* __restrict__ out, long long ldo,
+                   const float* __restrict__ bias_rel, int bias_ld, const int* __restrict__ key_mask, int L) {
+  extern __shared__ __align__(16) uint8_t t5m_smem[];
+  const T5MmaSmem lay = t5_mma_smem(L, D);
+  constexpr int KPB = D + 8;            // K pitch (bf16)
+  const int Lp = lay.Lp, VPB = Lp + 8;  // V^T pitch (bf16)
+  bf16* Ks = reinterpret_cast<bf16*>(t5m_smem + lay.k_off);
+  bf16* Vt = reinterpret_cast<bf16*>(t5m_smem + lay.v_off);
+  float* Bs = reinterpret_cast<float*>(t5m_smem + lay.bias_off);
+  uint8_t* Ms = t5m_smem + lay.mask_off;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long tok0 = (long long)b * L;
+  constexpr int VPR = D / 8;
+
+  // K rows (zero beyond L), 16 bytes per thread
+  for (int i = tid; i < Lp * VPR; i += kT5MmaThreads) {
+    const int row = i / VPR, cv = i - row * VPR;
+    uint4 kv = make_uint4(0, 0, 0, 0);
+    if (row < L) kv = __ldg(reinterpret_cast<const uint4*>(k + (tok0 + row) * ldk + h * D) + cv);
+    *reinterpret_cast<uint4*>(Ks + row * KPB + cv * 8) = kv;
+  }
+  // V transposed (zero beyond L): consecutive lanes take consecutive keys of one 8-channel group, so the 2-byte
+  // shared-memory stores of a warp are contiguous
+  for (int i = tid; i < Lp * VPR; i += kT5MmaThreads) {
+    const int cv = i / Lp, key = i - cv * Lp;
+    uint4 vv = make_uint4(0, 0, 0, 0);
+    if (key < L) vv = __ldg(reinterpret_cast<const uint4*>(v + (tok0 + key) * ldv + h * D) + cv);
+    const bf16* e = reinterpret_cast<const bf16*>(&vv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Vt[(cv * 8 + j) * VPB + key] = e[j];
+  }
+  for (int i = tid; i < 2 * L - 1; i += kT5MmaThreads) Bs[i] = __ldg(bias_rel + (long long)h * bias_ld + i);
+  for (int j = tid; j < Lp; j += kT5MmaThreads)
+    Ms[j] = (j < L && (key_mask == nullptr || key_mask[tok0 + j] != 0)) ? 1 : 0;
+  __syncthreads();
+
+  const int row0 = blockIdx.x * kT5MmaRows + warp * 16;
+  if (row0 >= L) return;
+  const int g = lane >> 2, t = lane & 3;
+  const int rA = row0 + g, rB = rA + 8;
+  const int iA = min(rA, L - 1), iB = min(rB, L - 1);    // bias row (rows beyond L are computed but never stored)
+
+  // Q fragments straight from global memory: [k-step][4]
+  uint32_t qf[D / 16][4];
+  {
+    const bf16* qa = q + (tok0 + iA) * ldq + h * D + 2 * t;
+    const bf16* qb = q + (tok0 + iB) * ldq + h * D + 2 * t;
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) {
+      qf[ks][0] = *reinterpret_cast<const uint32_t*>(qa + ks * 16);
+      qf[ks][1] = *reinterpret_cast<const uint32_t*>(qb + ks * 16);
+      qf[ks][2] = *reinterpret_cast<const uint32_t*>(qa + ks * 16 + 8);
+      qf[ks][3] = *reinterpret_cast<const uint32_t*>(qb + ks * 16 + 8);
+    }
+  }
+  const uint32_t* Kw = reinterpret_cast<const uint32_t*>(Ks);
+  const uint32_t* Vw = reinterpret_cast<const uint32_t*>(Vt);
+  const int nblk = Lp >> 6;
+
+  // scores of one 64-key block for this warp's 16 rows: s[nt][0..1] row rA, s[nt][2..3] row rB, keys kb*64+nt*8+2t(+1)
+  auto scores = [&](int kb, float (&s)[8][4]) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const int n = kb * 64 + nt * 8 + g;
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks) {
+        const uint32_t b0 = Kw[(n * KPB + ks * 16 + 2 * t) >> 1];
+        const uint32_t b1 = Kw[(n * KPB + ks * 16 + 8 + 2 * t) >> 1];
+        mma_bf16_16816(s[nt], qf[ks], b0, b1);
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = kb * 64 + nt * 8 + 2 * t + e;
+        if (j < L) {
+          const bool keep = Ms[j] != 0;
+          s[nt][e] += keep ? Bs[j - iA + L - 1] : VCOF_BF16_MIN;
+          s[nt][2 + e] += keep ? Bs[j - iB + L - 1] : VCOF_BF16_MIN;
+        } else {
+          s[nt][e] = -INFINITY;
+          s[nt][2 + e] = -INFINITY;
+        }
+      }
+    }
+  };
+
+  // pass 1: row max and sum of exponentials
+  float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;
+  for (int kb = 0; kb < nblk; ++kb) {
+    float s[8][4];
+    scores(kb, s);
+    float xa = -INFINITY, xb = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      xa = fmaxf(xa, fmaxf(s[nt][0], s[nt][1]));
+      xb = fmaxf(xb, fmaxf(s[nt][2], s[nt][3]));
+    }
+    xa = fmaxf(xa, __shfl_xor_sync(0xffffffffu, xa, 1)); xa = fmaxf(xa, __shfl_xor_sync(0xffffffffu, xa, 2));
+    xb = fmaxf(xb, __shfl_xor_sync(0xffffffffu, xb, 1)); xb = fmaxf(xb, __shfl_xor_sync(0xffffffffu, xb, 2));
+    const float nA = fmaxf(mA, xa), nB = fmaxf(mB, xb);   // finite: every block holds at least one key < L
+    lA *= __expf(mA - nA);
+    lB *= __expf(mB - nB);
+    mA = nA; mB = nB;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      lA += __expf(s[nt][0] - mA) + __expf(s[nt][1] - mA);
+      lB += __expf(s[nt][2] - mB) + __expf(s[nt][3] - mB);
+    }
+  }
+  lA += __shfl_xor_sync(0xffffffffu, lA, 1); lA += __shfl_xor_sync(0xffffffffu, lA, 2);
+  lB += __shfl_xor_sync(0xffffffffu, lB, 1); lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+  const float invA = 1.f / lA, invB = 1.f / lB;
+
+  // pass 2: P = bf16(exp(s - max) / sum) from the accumulator registers into P.V
+  float o[D / 8][4];
+#pragma unroll
+  for (int dn = 0; dn < D / 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+  for (int kb = 0; kb < nblk; ++kb) {
+    float s[8][4];
+    scores(kb, s);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {   // 16 keys = two adjacent 8-key tiles
+      uint32_t pf[4];
+      pf[0] = pack_bf16x2(__expf(s[2 * kk][0] - mA) * invA, __expf(s[2 * kk][1] - mA) * invA);
+      pf[1] = pack_bf16x2(__expf(s[2 * kk][2] - mB) * invB, __expf(s[2 * kk][3] - mB) * invB);
+      pf[2] = pack_bf16x2(__expf(s[2 * kk + 1][0] - mA) * invA, __expf(s[2 * kk + 1][1] - mA) * invA);
+      pf[3] = pack_bf16x2(__expf(s[2 * kk + 1][2] - mB) * invB, __expf(s[2 * kk + 1][3] - mB) * invB);
+      const int kbase = kb * 64 + kk * 16;
+#pragma unroll
+      for (int dn = 0; dn < D / 8; ++dn) {
+        const int n = dn * 8 + g;
+        const uint32_t b0 = Vw[(n * VPB + kbase + 2 * t) >> 1];
+        const uint32_t b1 = Vw[(n * VPB + kbase + 8 + 2 * t) >> 1];
+        mma_bf16_16816(o[dn], pf, b0, b1);
+      }
+    }
+  }
+  bf16* oa = out + (tok0 + rA) * ldo + h * D + 2 * t;
+  bf16* ob = out + (tok0 + rB) * ldo + h * D + 2 * t;
+#pragma unroll
+  for (int dn = 0; dn < D / 8; ++dn) {
+    if (rA < L) *reinterpret_cast<uint32_t*>(oa + dn * 8) = pack_bf16x2(o[dn][0], o[dn][1]);
+    if (rB < L) *reinterpret_cast<uint32_t*>(ob + dn * 8) = pack_bf16x2(o[dn][2], o[dn][3]);
+  }
+}
+
+template <int D>
+static int launch_t5_attn_mma(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                              void* out, long long ldo, const float* bias_rel, int bias_ld, const int* key_mask, int B,
+                              int L, int heads, cudaStream_t st) {
+  const T5MmaSmem lay = t5_mma_smem(L, D);
+  auto kern = t5_attn_mma_kernel<D>;
+  static int attr_bytes = 0;
+  if (lay.total > attr_bytes) {
+    VCOF_REQUIRE(lay.total <= 227 * 1024, "vcof_t5_attn: L=%d, head_dim=%d need %d B of shared memory", L, D, lay.total);
+    VCOF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+    attr_bytes = lay.total;
+  }
+  dim3 grid((L + kT5MmaRows - 1) / kT5MmaRows, heads, B);
+  kern<<<grid, kT5MmaThreads, lay.total, st>>>(
+      reinterpret_cast<const bf16*>(q), ldq, reinterpret_cast<const bf16*>(k), ldk, reinterpret_cast<const bf16*>(v),
+      ldv, reinterpret_cast<bf16*>(out), ldo, bias_rel, bias_ld, key_mask, L);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace vcof
 
 using namespace vcof;
@@ -271,6 +484,23 @@ extern "C" int vcof_t5_attn(const void* q, long long ldq, const void* k, long lo
   VCOF_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && B <= 65535 && heads <= 65535,
                "vcof_t5_attn: ldq/ldk/ldv must be multiples of 8 (16-byte rows)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // VCOF_T5_ATTN=mma|simple selects the tensor-core (mma.sync) or the CUDA-core kernel
+  static const bool use_mma = [] {
+    const char* e = getenv("VCOF_T5_ATTN");
+    return e != nullptr ? (e[0] == 'm') : VCOF_T5_ATTN_DEFAULT_MMA;
+  }();
+  if (use_mma) {
+    VCOF_REQUIRE(ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0, "vcof_t5_attn: out must be 4-byte aligned");
+    switch (head_dim) {
+      case 16: return launch_t5_attn_mma<16>(q, ldq, k, ldk, v, ldv, out, ldo, bias_rel, bias_ld, key_mask, B, L, heads, st);
+      case 32: return launch_t5_attn_mma<32>(q, ldq, k, ldk, v, ldv, out, ldo, bias_rel, bias_ld, key_mask, B, L, heads, st);
+      case 64: return launch_t5_attn_mma<64>(q, ldq, k, ldk, v, ldv, out, ldo, bias_rel, bias_ld, key_mask, B, L, heads, st);
+      case 128: return launch_t5_attn_mma<128>(q, ldq, k, ldk, v, ldv, out, ldo, bias_rel, bias_ld, key_mask, B, L, heads, st);
+      default: break;
+    }
+    set_last_error("vcof_t5_attn: head_dim %d not in {16, 32, 64, 128}", head_dim);
+    return -1;
+  }
   switch (head_dim) {
     case 16: return launch_t5_attn<16>(q, ldq, k, ldk, v, ldv, out, ldo, bias_rel, bias_ld, key_mask, B, L, heads, st);
     case 32: return launch_t5_attn<32>(q, ldq, k, ldk, v, ldv, out, ldo, bias_rel, bias_ld, key_mask, B, L, heads, st);
