@@ -50,19 +50,31 @@ def resolve(layer_token, weight_names):
     underscore-joined form equals the token."""
     if "lora_te" in layer_token:
         return None
-    flat = layer_token.split("lora_unet_")[-1].lstrip("_")
+    return _by_flat_name(layer_token.split("lora_unet_")[-1].lstrip("_"), weight_names)
+
+
+def resolve_text_encoder(layer_token, weight_names):
+    """The same search rooted at pipeline.text_encoder for `lora_te_…` tokens (:406-411): on the umT5 encoder
+    (wan_text_encoder.py) `lora_te_blocks_3_ffn_gate_0` lands on blocks.3.ffn.gate.0."""
+    if "lora_te" not in layer_token:
+        return None
+    return _by_flat_name(layer_token.split("lora_te_")[-1].lstrip("_"), weight_names)
+
+
+def _by_flat_name(flat, weight_names):
     for name in weight_names:
         if name.replace(".", "_") == flat:
             return name
     return None
 
 
-def merge(weights, state_dict, multiplier, dtype=torch.float32, sign=1.0):
+def merge(weights, state_dict, multiplier, dtype=torch.float32, sign=1.0, text_encoder=False):
     """weights: {module path: weight tensor (e.g. bf16)} for every module that owns a `.weight`.  Returns the names it
-    updated; tensors are replaced by new ones of the original dtype (:482-497)."""
+    updated; tensors are replaced by new ones of the original dtype (:482-497).  With text_encoder=True `weights` are
+    the text encoder's and only `lora_te_…` entries apply."""
     touched = []
     for layer, elems in normalise_keys(state_dict).items():
-        name = resolve(layer, list(weights))
+        name = (resolve_text_encoder if text_encoder else resolve)(layer, list(weights))
         if name is None:
             continue
         if "lora_up.weight" not in elems or "lora_down.weight" not in elems:
@@ -107,4 +119,16 @@ def make_lora_state(weight_shapes, rank=8, seed=0, dtype=torch.float32):
     sd["diffusion_model.blocks.99.self_attn.q.lora_up.weight"] = rnd(4, rank, std=1.0)
     sd["lora_te_encoder_block_0_layer_0_SelfAttention_q.lora_down.weight"] = rnd(rank, 4, std=1.0)
     sd["lora_te_encoder_block_0_layer_0_SelfAttention_q.lora_up.weight"] = rnd(4, rank, std=1.0)
+    return sd
+
+
+def make_te_lora_state(weight_shapes, rank=4, seed=0, dtype=torch.float32):
+    """kohya-style `lora_te_<underscored module path>` entries (with alpha) for every Linear of a umT5 encoder."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, (n_out, k_in) in weight_shapes.items():
+        base = "lora_te_" + name.replace(".", "_")
+        sd[base + ".lora_down.weight"] = (torch.randn(rank, k_in, generator=g) / math.sqrt(k_in)).to(dtype)
+        sd[base + ".lora_up.weight"] = (torch.randn(n_out, rank, generator=g) * 0.05).to(dtype)
+        sd[base + ".alpha"] = torch.tensor(float(rank) / 2)
     return sd

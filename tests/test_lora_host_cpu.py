@@ -77,3 +77,41 @@ def test_overlay_exports_merge_entry_points():
     import videox_fun.utils.lora_utils as m
     from videocof_b200 import lora
     assert m.merge_lora is lora.merge_lora and m.unmerge_lora is lora.unmerge_lora
+
+
+def test_text_encoder_entries_merge_into_our_encoder(monkeypatch, tmp_path):
+    """`lora_te_…` entries land on videocof_b200.text_encoder.WanT5EncoderModel's Linears exactly as the reference
+    lands them on its own encoder (bit-exact CRCs from the executed reference, tools/gen_golden_lora_te.py);
+    transformer_only=True skips them."""
+    from safetensors.torch import save_file
+    from gen_golden_lora_te import MULT as M_TE, RANK as R_TE, te_linear_shapes
+    from gen_golden_pipeline import T5_KW
+    from oracle.lora_oracle import make_te_lora_state
+    from oracle.t5_oracle import T5Config, make_t5_params
+    from videocof_b200 import lora
+    from videocof_b200.text_encoder import WanT5EncoderModel
+    monkeypatch.setattr(lora, "_apply", _contract_apply)
+    tcfg = T5Config(**T5_KW)
+    params = make_t5_params(tcfg, seed=19)
+    t5 = WanT5EncoderModel(**tcfg.to_kwargs())
+    t5.load_state_dict(params, strict=True)
+    t5 = t5.to(torch.bfloat16)
+    dit, _, _ = _model_and_state()
+    sd = make_te_lora_state(te_linear_shapes(params), rank=R_TE, seed=9)
+    pipe = types.SimpleNamespace(transformer=dit, text_encoder=t5)
+    before = {k: v.clone() for k, v in t5.state_dict().items()}
+    lora.merge_lora(pipe, None, M_TE, device="cpu", state_dict=dict(sd), transformer_only=True)
+    assert all(torch.equal(v, before[k]) for k, v in t5.state_dict().items())
+    lora.merge_lora(pipe, None, M_TE, device="cpu", state_dict=dict(sd))
+    g = np.load(os.path.join(os.path.dirname(GOLD), "lora_te_tiny.npz"))
+    changed = [str(k) for k in g["changed"]]
+    state = t5.state_dict()
+    for k, crc in zip(changed, g["crc_merged"]):
+        assert zlib.crc32(_bits(state[k]).tobytes()) == int(crc), k
+    assert all(torch.equal(v, before[k]) for k, v in state.items() if k not in changed)
+    path = str(tmp_path / "te.safetensors")
+    save_file({k: v.contiguous() for k, v in sd.items()}, path)
+    lora.unmerge_lora(pipe, path, M_TE, device="cpu")
+    state = t5.state_dict()
+    for k, crc in zip(changed, g["crc_unmerged"]):
+        assert zlib.crc32(_bits(state[k]).tobytes()) == int(crc), k

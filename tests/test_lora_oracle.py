@@ -50,3 +50,25 @@ def test_merge_and_unmerge_match_reference_bits():
     merge(weights, {k: v for k, v in sd.items() if not k.startswith("lora_te")}, MULT, sign=-1.0)
     for k, crc in zip(changed, g["crc_unmerged"]):
         assert zlib.crc32(_bits(weights[k[:-7]]).tobytes()) == int(crc), k
+
+
+def test_text_encoder_entries_match_reference_bits():
+    """`lora_te_…` tokens resolve under pipeline.text_encoder (lora_utils.py:406-411); golden from the executed
+    reference on its own umT5 encoder (tools/gen_golden_lora_te.py)."""
+    from gen_golden_lora_te import MULT as M_TE, RANK as R_TE, te_linear_shapes
+    from gen_golden_pipeline import T5_KW
+    from oracle.lora_oracle import make_te_lora_state
+    from oracle.t5_oracle import T5Config, make_t5_params
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lora_te_tiny.npz"))
+    params = make_t5_params(T5Config(**T5_KW), seed=19)
+    sd = make_te_lora_state(te_linear_shapes(params), rank=R_TE, seed=9)
+    weights = {k[:-7]: v.to(torch.bfloat16) for k, v in params.items() if k.endswith(".weight")}
+    touched = merge(weights, sd, M_TE, text_encoder=True)
+    changed = [str(k) for k in g["changed"]]
+    assert sorted(t + ".weight" for t in touched) == changed
+    for k, crc in zip(changed, g["crc_merged"]):
+        assert zlib.crc32(_bits(weights[k[:-7]]).tobytes()) == int(crc), k
+    merge(weights, sd, M_TE, sign=-1.0, text_encoder=True)
+    for k, crc in zip(changed, g["crc_unmerged"]):
+        assert zlib.crc32(_bits(weights[k[:-7]]).tobytes()) == int(crc), k
+    assert merge(dict(weights), sd, M_TE) == []                       # the DiT search ignores lora_te entries

@@ -1,4 +1,4 @@
-"""On-device LoRA merge for the DiT: `merge_lora` / `unmerge_lora` with the reference's signatures
+"""On-device LoRA merge for the DiT (and the umT5 text encoder): `merge_lora` / `unmerge_lora` with the reference's signatures
 (videox_fun/utils/lora_utils.py:371 and :503; called by fast_infer.py:371-385, :449).
 
 The reference lifts every target Linear to fp32 on `device`, adds `multiplier * alpha/rank * up @ down` and casts
@@ -89,15 +89,19 @@ def _run(pipeline, state_dict, multiplier, device, dtype, transformer_only, sub_
                                   f"(got dtype={dtype})")
     root = getattr(pipeline, sub_transformer_name)
     index = _module_index(root)
+    te = getattr(pipeline, "text_encoder", None)
+    te_index = None
     merged = 0
     with torch.no_grad():
         for layer, elems in _group_keys(state_dict).items():
             if _PREFIX_TE in layer:
-                if transformer_only or getattr(pipeline, "text_encoder", None) is None:
+                # `lora_te_…` tokens resolve under pipeline.text_encoder (lora_utils.py:406-411)
+                if transformer_only or te is None:
                     continue
-                raise NotImplementedError("merge_lora: text-encoder LoRA entries are outside the B200 hot path "
-                                          "(SURVEY.md §8f); pass transformer_only=True")
-            mod = index.get(layer.split(_PREFIX_DIT + "_")[-1].lstrip("_"))
+                te_index = _module_index(te) if te_index is None else te_index
+                mod = te_index.get(layer.split(_PREFIX_TE + "_")[-1].lstrip("_"))
+            else:
+                mod = index.get(layer.split(_PREFIX_DIT + "_")[-1].lstrip("_"))
             if mod is None:
                 print(f"Error loading layer: {layer}")            # the reference logs and moves on (:425-459)
                 continue
