@@ -519,7 +519,33 @@ static int launch_gemm2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     attr_set = true;
   }
   const int num_tiles = ((args.M + 2 * kBM - 1) / (2 * kBM)) * ((args.N + Gemm2Cfg::kBN - 1) / Gemm2Cfg::kBN);
-  int grid = 2 * num_tiles < sm_count() ? 2 * num_tiles : (sm_count() & ~1);
+  // A persistent kernel must not launch more CTA pairs than can be co-resident: a pair needs both SMs of one TPC,
+  // and a part with 148 of its SMs enabled need not have 74 complete TPCs.  Pairs beyond the resident set would run
+  // as a second wave with a full share of the tiles each — the first version sized the grid as sm_count / 2 pairs
+  // and measured exactly half the single-CTA throughput (profiles/r1_gpurun34_gemm_2cta.log).
+  static int max_pairs = 0;
+  if (max_pairs == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sm_count() & ~1);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Gemm2Cfg::kSmemBytes;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = sm_count() / 2;
+    }
+    const char* e = getenv("VCOF_GEMM_2CTA_PAIRS");     // override for experiments
+    if (e != nullptr && atoi(e) > 0) n = atoi(e);
+    max_pairs = n < sm_count() / 2 ? n : sm_count() / 2;
+  }
+  const int grid = 2 * (num_tiles < max_pairs ? num_tiles : max_pairs);
   kern<<<grid, kGemmThreads, Gemm2Cfg::kSmemBytes, stream>>>(tmA, tmB, args);
   VCOF_CHECK_CUDA(cudaGetLastError());
   return 0;
