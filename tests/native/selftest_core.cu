@@ -1,0 +1,159 @@
+// selftest_core.cu — stand-alone parity check of the two tensor-core kernels of the denoising step over the C ABI
+// (no Python): vcof_gemm_bf16 (bias / GELU / gated fp32 residual / fp32 store epilogues) and vcof_attn_fwd
+// (head_dim 128, ragged lengths, kv_len < Lk, V^T input) against double-precision CPU restatements in this file.
+// Meant for kernel work: `VCOF_GEMM_2CTA=1 tests/native/selftest_core gemm`, `VCOF_ATTN_EMU=2 … attn` validate a
+// variant in seconds of GPU time.  The Python suite (tests/test_kernels_gpu.py) stays the reference gate.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/vcof.h"
+
+typedef __nv_bfloat16 bf16;
+static uint64_t g_seed = 0x243F6A8885A308D3ull;
+static double urand() {
+  g_seed ^= g_seed >> 12; g_seed ^= g_seed << 25; g_seed ^= g_seed >> 27;
+  return ((g_seed * 0x2545F4914F6CDD1Dull) >> 11) * (1.0 / 9007199254740992.0) + 1e-17;
+}
+static double nrand() { return sqrt(-2.0 * log(urand())) * cos(6.283185307179586 * urand()); }
+static float bfr(double x) { return __bfloat162float(__float2bfloat16_rn((float)x)); }
+static std::vector<bf16> rand_bf16(size_t n, double scale) {
+  std::vector<bf16> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = __float2bfloat16_rn((float)(scale * nrand()));
+  return v;
+}
+template <class T> static T* to_dev(const std::vector<T>& h) {
+  T* d = nullptr;
+  if (cudaMalloc(&d, h.size() * sizeof(T)) != cudaSuccess) { fprintf(stderr, "cudaMalloc failed\n"); exit(2); }
+  cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return d;
+}
+template <class T> static std::vector<T> to_host(const T* d, size_t n) {
+  std::vector<T> h(n);
+  cudaMemcpy(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost);
+  return h;
+}
+static int g_fail = 0;
+static void report(const char* name, const char* shape, const std::vector<double>& got, const std::vector<double>& ref,
+                   double tol, int rc) {
+  double num = 0, den = 0;
+  bool nan = false;
+  for (size_t i = 0; i < ref.size(); ++i) {
+    if (got[i] != got[i]) nan = true;
+    num += (got[i] - ref[i]) * (got[i] - ref[i]);
+    den += ref[i] * ref[i];
+  }
+  const double rel = sqrt(num / (den + 1e-300));
+  const cudaError_t e = cudaDeviceSynchronize();
+  const bool ok = rc == 0 && e == cudaSuccess && !nan && rel < tol;
+  if (!ok) ++g_fail;
+  printf("{\"case\": \"%s\", \"shape\": \"%s\", \"rc\": %d, \"cuda\": %d, \"rel_fro\": %.3e, \"tol\": %.1e, \"nan\": %s, "
+         "\"ok\": %s%s%s%s}\n", name, shape, rc, (int)e, rel, tol, nan ? "true" : "false", ok ? "true" : "false",
+         rc ? ", \"error\": \"" : "", rc ? vcof_last_error() : "", rc ? "\"" : "");
+  fflush(stdout);
+}
+static double gelu_tanh(double x) { return 0.5 * x * (1.0 + tanh(0.7978845608028654 * (x + 0.044715 * x * x * x))); }
+
+static void case_gemm(int M, int N, int K, int epi) {
+  auto a = rand_bf16((size_t)M * K, 1.0), w = rand_bf16((size_t)N * K, 1.0 / sqrt((double)K)), bias = rand_bf16(N, 1.0);
+  std::vector<float> gate(N), x0((size_t)M * N);
+  for (auto& g : gate) g = (float)nrand();
+  for (auto& v : x0) v = (float)nrand();
+  bf16 *da = to_dev(a), *dw = to_dev(w), *db = to_dev(bias);
+  float* dg = to_dev(gate);
+  const bool f32 = epi == VCOF_EPI_BIAS_GATE_RES_F32 || epi == VCOF_EPI_BIAS_F32;
+  void* dout = nullptr;
+  if (f32) dout = to_dev(x0); else cudaMalloc(&dout, (size_t)M * N * 2);
+  const int rc = vcof_gemm_bf16(da, K, dw, K, db, epi == VCOF_EPI_BIAS_GATE_RES_F32 ? dg : nullptr, dout, N, M, N, K, epi, nullptr);
+  std::vector<double> got((size_t)M * N), ref((size_t)M * N);
+  if (f32) { auto h = to_host((float*)dout, (size_t)M * N); for (size_t i = 0; i < h.size(); ++i) got[i] = h[i]; }
+  else { auto h = to_host((bf16*)dout, (size_t)M * N); for (size_t i = 0; i < h.size(); ++i) got[i] = __bfloat162float(h[i]); }
+  std::vector<float> af((size_t)M * K), wf((size_t)N * K);
+  for (size_t i = 0; i < af.size(); ++i) af[i] = __bfloat162float(a[i]);
+  for (size_t i = 0; i < wf.size(); ++i) wf[i] = __bfloat162float(w[i]);
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double acc = __bfloat162float(bias[n]);
+      const float *ar = &af[(size_t)m * K], *wr = &wf[(size_t)n * K];
+      for (int k = 0; k < K; ++k) acc += (double)ar[k] * wr[k];
+      const size_t i = (size_t)m * N + n;
+      ref[i] = epi == VCOF_EPI_BIAS_BF16 ? acc : epi == VCOF_EPI_BIAS_GELU_BF16 ? gelu_tanh(bfr(acc))
+               : epi == VCOF_EPI_BIAS_GATE_RES_F32 ? x0[i] + (double)gate[n] * bfr(acc) : (double)bfr(acc);
+    }
+  char shape[64]; snprintf(shape, sizeof shape, "M=%d N=%d K=%d epi=%d", M, N, K, epi);
+  report("gemm", shape, got, ref, 6e-3, rc);
+  cudaFree(da); cudaFree(dw); cudaFree(db); cudaFree(dg); cudaFree(dout);
+}
+
+static void case_attn(int Lq, int Lk, int kv, int heads, int vt) {
+  const int C = heads * 128;
+  auto q = rand_bf16((size_t)Lq * C, 1.0), k = rand_bf16((size_t)Lk * C, 1.0), v = rand_bf16((size_t)Lk * C, 1.0);
+  bf16 *dq = to_dev(q), *dk = to_dev(k), *dv = nullptr, *dout = nullptr;
+  long long ldv = C;
+  if (vt) {                                         // V^T [C, ldv] with kv contiguous
+    ldv = (Lk + 7) / 8 * 8;
+    std::vector<bf16> t((size_t)C * ldv, __float2bfloat16_rn(0.f));
+    for (int j = 0; j < Lk; ++j) for (int c = 0; c < C; ++c) t[(size_t)c * ldv + j] = v[(size_t)j * C + c];
+    dv = to_dev(t);
+  } else {
+    dv = to_dev(v);
+  }
+  cudaMalloc(&dout, (size_t)Lq * C * 2);
+  const int rc = vcof_attn_fwd(dq, C, dk, C, dv, ldv, dout, C, Lq, Lk, kv, heads, 128, (float)(1.0 / sqrt(128.0)), vt, nullptr);
+  auto h = to_host(dout, (size_t)Lq * C);
+  std::vector<double> got((size_t)Lq * C), ref((size_t)Lq * C), s(kv);
+  for (size_t i = 0; i < h.size(); ++i) got[i] = __bfloat162float(h[i]);
+  for (int hd = 0; hd < heads; ++hd)
+    for (int i = 0; i < Lq; ++i) {
+      double mx = -INFINITY, sum = 0;
+      for (int j = 0; j < kv; ++j) {
+        double acc = 0;
+        for (int c = 0; c < 128; ++c)
+          acc += (double)__bfloat162float(q[(size_t)i * C + hd * 128 + c]) * __bfloat162float(k[(size_t)j * C + hd * 128 + c]);
+        s[j] = acc / sqrt(128.0);
+        mx = fmax(mx, s[j]);
+      }
+      for (int j = 0; j < kv; ++j) { s[j] = exp(s[j] - mx); sum += s[j]; }
+      for (int c = 0; c < 128; ++c) {
+        double acc = 0;
+        for (int j = 0; j < kv; ++j) acc += s[j] * __bfloat162float(v[(size_t)j * C + hd * 128 + c]);
+        ref[(size_t)i * C + hd * 128 + c] = acc / sum;
+      }
+    }
+  char shape[96]; snprintf(shape, sizeof shape, "Lq=%d Lk=%d kv=%d heads=%d vt=%d", Lq, Lk, kv, heads, vt);
+  report("attn", shape, got, ref, 1.5e-2, rc);
+  cudaFree(dq); cudaFree(dk); cudaFree(dv); cudaFree(dout);
+}
+
+int main(int argc, char** argv) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { puts("{\"error\": \"no CUDA device\"}"); return 3; }
+  const bool all = argc < 2;
+  if (all || strcmp(argv[1], "gemm") == 0) {
+    const int shapes[5][3] = {{128, 256, 64}, {300, 512, 256}, {640, 1536, 512}, {777, 1024, 320}, {512, 64, 1024}};
+    for (auto& sh : shapes)
+      for (int epi : {VCOF_EPI_BIAS_BF16, VCOF_EPI_BIAS_GELU_BF16, VCOF_EPI_BIAS_GATE_RES_F32, VCOF_EPI_BIAS_F32})
+        case_gemm(sh[0], sh[1], sh[2], epi);
+    case_gemm(200, 104, 64, VCOF_EPI_BIAS_BF16);
+    case_gemm(200, 304, 192, VCOF_EPI_BIAS_GATE_RES_F32);
+    case_gemm(2048, 2560, 512, VCOF_EPI_BIAS_BF16);      // several waves of tiles per CTA
+  }
+  if (all || strcmp(argv[1], "attn") == 0) {
+    for (int vt = 0; vt < 2; ++vt) {
+      case_attn(128, 128, 128, 1, vt);
+      case_attn(300, 336, 336, 2, vt);
+      case_attn(512, 640, 600, 2, vt);
+      case_attn(1280, 1280, 1280, 2, vt);
+    }
+    case_attn(300, 333, 333, 2, 0);
+    case_attn(2304, 512, 512, 20, 0);                    // > 148 work items: persistent CTAs walk several items
+  }
+  printf("{\"failed\": %d}\n", g_fail);
+  return g_fail ? 1 : 0;
+}

@@ -67,3 +67,25 @@ def test_rejects_cpu_weights_bad_ids_and_3d_masks(monkeypatch):
         model(torch.full_like(ids, cfg.vocab))
     with pytest.raises(NotImplementedError):
         model(ids, attention_mask=torch.ones(1, ids.shape[1], ids.shape[1]))
+
+
+def test_from_pretrained_filters_kwargs_and_loads(tmp_path, monkeypatch):
+    """fast_infer.py:321-326 passes the whole `text_encoder_kwargs` YAML block (config/wan2.1/wan_civitai.yaml:14-26:
+    sub-paths, text_length, … next to the constructor arguments) and a single .pth / .safetensors state dict."""
+    from safetensors.torch import save_file
+    cfg, params, _, (ids, mask) = build("t5_tiny")
+    kw = dict(cfg.to_kwargs(), text_encoder_subpath="x.pth", tokenizer_subpath="google/umt5-xxl", text_length=512)
+    pth, st = str(tmp_path / "t5.pth"), str(tmp_path / "t5.safetensors")
+    torch.save(params, pth)
+    save_file({k: v.contiguous() for k, v in params.items()}, st)
+    for path in (pth, st):
+        m = WanT5EncoderModel.from_pretrained(path, additional_kwargs=kw, low_cpu_mem_usage=True,
+                                              torch_dtype=torch.bfloat16)
+        assert m.dtype == torch.bfloat16 and m.device.type == "cpu" and not m.training
+        sd = m.state_dict()
+        assert set(sd) == set(params)
+        assert all(torch.equal(sd[k], params[k].to(torch.bfloat16)) for k in params)
+    vcof_emulator.install_t5(monkeypatch)
+    ref = t5_forward(params, cfg, ids, mask, emulate_bf16=True)
+    out = m(ids, attention_mask=mask)[0]
+    assert float((out.float() - ref).norm() / ref.norm()) < 6e-3
