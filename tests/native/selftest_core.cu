@@ -152,7 +152,7 @@ int main(int argc, char** argv) {
       case_attn(1280, 1280, 1280, 2, vt);
     }
     case_attn(300, 333, 333, 2, 0);
-    case_attn(2304, 512, 512, 20, 0);                    // > 148 work items: persistent CTAs walk several items
+    case_attn(1024, 128, 128, 40, 0);                    // 160 work items > 148 SMs: persistent CTAs walk several items
   }
   printf("{\"failed\": %d}\n", g_fail);
   return g_fail ? 1 : 0;
