@@ -77,7 +77,12 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // SPLIT_S: S_t = Q_t K_j^T is issued as two N=64 halves with separate barriers, so the softmax warps load and
 // reduce the first 64 score columns while the tensor pipe still computes the second half.
 // PSPLIT: number of K-chunks (2 or 4) in which P is published to the PV MMA.
-template <bool V_TRANS, int EMU, bool SPLIT_S, int PSPLIT>
+// SPEC (experimental, VCOF_ATTN_SPEC=1, not yet run on hardware): the row maximum leaves the critical path.  The
+// exponentials of a tile start against the STALE reference maximum as soon as the scores are in registers; the
+// maximum of the shifted scores is folded into the loop of the first 64 exponentials (ALU pipe, hidden under MUFU)
+// and only if some row outgrew the reference by more than 2^8 — the same condition under which the default kernel
+// rescales — is the tile redone against the advanced reference.  Same arithmetic as the default path otherwise.
+template <bool V_TRANS, int EMU, bool SPLIT_S, int PSPLIT, bool SPEC = false>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
@@ -302,6 +307,107 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int q0 = (item % p.num_q_blocks) * 2 * kQT;
       float m_ref = -INFINITY;  // running (possibly stale) row max, raw score units
       float l = 0.f;
+      if constexpr (SPEC) {
+        static_assert(!SPEC || (EMU == 0 && !SPLIT_S && PSPLIT == 2), "SPEC builds on the default variant");
+        float mb = -INFINITY;   // running (possibly stale) row max in scaled log2 units
+        for (int j = 0; j < n_kv; ++j) {
+          uint32_t s[128];
+          mbar_wait(s_full + 8 * t, sph);
+          tc_fence_after();
+          sph ^= 1;
+          tmem_ld32(tS + 0, s + 0);
+          tmem_ld32(tS + 32, s + 32);
+          tmem_ld32(tS + 64, s + 64);
+          tmem_ld32(tS + 96, s + 96);
+          tmem_ld_wait();
+          if (j == n_kv - 1 && rem < kKT) {
+#pragma unroll
+            for (int c = 0; c < 128; ++c)
+              if (c >= rem) s[c] = 0xff800000u;  // -inf
+          }
+          if (j == 0) {   // first tile: no reference yet, the maximum has to come first
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 128; c += 4) {
+              mx0 = fmaxf(mx0, __uint_as_float(s[c]));
+              mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+              mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
+              mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+            }
+            mb = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+          }
+          const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+          const float2 nmb2 = make_float2(-mb, -mb);
+          float2 x[64];
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            x[c] = __ffma2_rn(make_float2(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1])), sc2, nmb2);
+          float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+          uint32_t pk[32];
+          float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float2 pr;
+            pr.x = ex2(x[c].x);
+            pr.y = ex2(x[c].y);
+            if (c & 1) acc1 = __fadd2_rn(acc1, pr); else acc0 = __fadd2_rn(acc0, pr);
+            pk[c] = pack_bf16x2(pr.x, pr.y);
+            mxa = fmaxf(fmaxf(mxa, x[c].x), x[c].y);
+            mxb = fmaxf(fmaxf(mxb, x[32 + c].x), x[32 + c].y);
+          }
+          const float mxx = fmaxf(mxa, mxb);
+          if (j > 0 && __any_sync(0xffffffffu, mxx > kRescaleThresh)) {
+            // rare: advance the reference by d (per row), rescale O_t and l, redo the first half.  PV_t(j-1) retired
+            // before s_full fired and PV_t(j) is not issued until we arrive on p_part: O_t is ours to rescale.
+            const float d = fmaxf(mxx, 0.f);
+            const float alpha = ex2(-d);
+            l *= alpha;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st32(tO + c * 32, o);
+            }
+            tmem_st_wait();
+            mb += d;
+            const float2 nd2 = make_float2(-d, -d);
+#pragma unroll
+            for (int c = 0; c < 64; ++c) x[c] = __fadd2_rn(x[c], nd2);
+            acc0 = make_float2(0.f, 0.f);
+            acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              float2 pr;
+              pr.x = ex2(x[c].x);
+              pr.y = ex2(x[c].y);
+              if (c & 1) acc1 = __fadd2_rn(acc1, pr); else acc0 = __fadd2_rn(acc0, pr);
+              pk[c] = pack_bf16x2(pr.x, pr.y);
+            }
+          }
+          tmem_st32(tS, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_part + 8 * (0 * 2 + t));
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float2 pr;
+            pr.x = ex2(x[32 + c].x);
+            pr.y = ex2(x[32 + c].y);
+            if (c & 1) acc1 = __fadd2_rn(acc1, pr); else acc0 = __fadd2_rn(acc0, pr);
+            pk[c] = pack_bf16x2(pr.x, pr.y);
+          }
+          tmem_st32(tS + 32, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_part + 8 * (1 * 2 + t));
+          l += (acc0.x + acc1.x) + (acc0.y + acc1.y);
+        }
+      } else
       for (int j = 0; j < n_kv; ++j) {
         uint32_t s[128];
         mbar_wait(s_full + 8 * t, sph);
@@ -480,8 +586,14 @@ extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long l
     const char* q = getenv("VCOF_ATTN_PSPLIT");
     psplit = (q && atoi(q) == 4) ? 4 : 2;
   }
+  static const bool spec = [] {
+    const char* e = getenv("VCOF_ATTN_SPEC");
+    return e != nullptr && e[0] == '1';
+  }();
   int lrc = 0;
-  if (emu == 3 || split_s) {            // experimental variants, natural-V layout only
+  if (spec && emu == 0 && !split_s && psplit == 2) {   // experimental: row maximum off the critical path
+    lrc = v_transposed ? launch(attn_fwd_kernel<true, 0, false, 2, true>) : launch(attn_fwd_kernel<false, 0, false, 2, true>);
+  } else if (emu == 3 || split_s) {            // experimental variants, natural-V layout only
     VCOF_REQUIRE(!v_transposed, "vcof_attn_fwd: tuning variants support the natural V layout only");
     if (emu == 3) lrc = launch(attn_fwd_kernel<false, 3, false, 2>);
     else lrc = launch(attn_fwd_kernel<false, 0, true, 2>);
