@@ -1,0 +1,34 @@
+#!/bin/bash
+# First GPU call of a kernel-tuning session: parity of the core kernels for every queued variant, then the A/B timings
+# that decide them.  Python-free, ~1 minute of box time:
+#     gpurun --timeout 150 -- 'bash tools/r2_first_call.sh'
+# Results land in gpurun_out/r2_first_call.jsonl (one JSON object per line, knobs recorded in each line).
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+OUT=gpurun_out/r2_first_call.jsonl
+: > "$OUT"
+export KBENCH_OUT="$OUT"
+run() { echo "### $*" | tee -a "$OUT"; timeout 60 "$@" | tee -a "$OUT"; }
+
+# 1. parity gates (default build first: it must stay green)
+run tests/native/selftest_core
+VCOF_ATTN_SPEC=1 run tests/native/selftest_core attn
+VCOF_GEMM_2CTA=1 run tests/native/selftest_core gemm
+
+# 2. attention, C2 shape on 8 heads (1/5 of a launch: same per-SM work, 5x less box time)
+run tests/native/kbench attn 75600 75600 8 3
+VCOF_ATTN_SPEC=1 run tests/native/kbench attn 75600 75600 8 3
+
+# 3. GEMM, the three DiT shapes; pair kernel with the occupancy-sized grid, then a sweep of the pair count
+for shape in "75600 5120 5120 0" "75600 13824 5120 1" "75600 5120 13824 2"; do
+  run tests/native/kbench gemm $shape 10
+  VCOF_GEMM_2CTA=1 run tests/native/kbench gemm $shape 10
+done
+for pairs in 60 64 68 70 72 74; do
+  VCOF_GEMM_2CTA=1 VCOF_GEMM_2CTA_PAIRS=$pairs run tests/native/kbench gemm 75600 5120 5120 0 10
+done
+
+# 4. text encoder end to end
+run tests/native/selftest_t5 --bench "$OUT"
+echo done
