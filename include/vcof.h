@@ -198,6 +198,19 @@ int vcof_t5_attn(const void* q, long long ldq, const void* k, long long ldk, con
                  long long ldo, const float* bias_rel, int bias_ld, const int* key_mask, int B, int L, int heads,
                  int head_dim, void* stream);
 
+/* ---- frame bytes at the two ends of the pipeline ------------------------------------ */
+
+/* out_u8[npos, C] = trunc(255 * clamp(bf16(bf16(x / 2) + 0.5), 0, 1)) for the first C channels of channels-last bf16
+ * x[npos, ldx] (the decoder output, C = 3): WanPipeline.decode_latents' bf16 (frames / 2 + 0.5).clamp(0, 1)
+ * (pipeline_wan.py:425-426) + .cpu().float() (:427) + save_videos_grid's (x * 255).astype(uint8)
+ * (videox_fun/utils/utils.py:59-68) in one pass; [T, H, W, 3] byte frames come out ready for the encoder. Bit-exact. */
+int vcof_cl_to_u8(const void* x, long long ldx, unsigned char* out, long long npos, int C, void* stream);
+
+/* y_bf16[npos, Cp] (channels-last, channels >= C zero) = bf16(fp32(u) * fp32(2/255) - 1) from byte frames
+ * frames[npos, C]: load_video_frames' scaling (fast_infer.py:86-88) + the cast to the VAE dtype (pipeline_wan.py:397)
+ * + the NCHW -> channels-last pass of the encoder's first layer.  Bit-exact. */
+int vcof_u8_to_cl(const unsigned char* frames, void* y, long long npos, int C, int Cp, void* stream);
+
 /* ---- diagnostics ---------------------------------------------------------------------- */
 /* One 128x128x64 tcgen05 tile with hand-swizzled operands (no TMA): d_f32[128,128] =
  * a_bf16[128,64] x b_bf16[128,64]^T.  mode bit0: B staged MN-major; bit1: A fed from TMEM.
@@ -212,6 +225,11 @@ int vcof_debug_umma_probe(const void* a, const void* b, float* d, int mode, void
 int vcof_debug_tma_probe(const void* base, int rank, const long long* dims, const long long* strides, const int* box,
                          int swizzle_bytes, int iters, const int* coords, int step_dim, int step, int wrap,
                          unsigned long long* cycles, int grid, int producers, int flags, void* stream);
+
+/* The per-element functions of vcof_cl_to_u8 / vcof_u8_to_cl evaluated on the HOST over host arrays (bf16 values as
+ * raw 16-bit patterns): the CPU test suite pins the kernels' arithmetic exhaustively.  No product code calls these. */
+int vcof_debug_frame_u8_host(const unsigned short* host_bf16_bits, unsigned char* host_out, long long n);
+int vcof_debug_video_bf16_host(const unsigned char* host_bytes, unsigned short* host_bf16_bits, long long n);
 
 #ifdef __cplusplus
 }

@@ -147,6 +147,33 @@ def cl_to_nchw(x, C, sub=None, mul=None):
     return v.permute(3, 0, 1, 2).contiguous().to(torch.bfloat16)
 
 
+def u8_to_cl(frames, Cp):
+    """vcof_u8_to_cl through the library's HOST evaluation of the kernel's own per-element function."""
+    import numpy as np
+    from videocof_b200 import _lib
+    T, H, W, C = frames.shape
+    src = np.ascontiguousarray(frames.numpy())
+    bits = np.empty(src.shape, dtype=np.uint16)
+    _lib.call("vcof_debug_video_bf16_host", src.ctypes.data, bits.ctypes.data, src.size)
+    y = torch.zeros(T, H, W, Cp, dtype=torch.bfloat16)
+    y[..., :C] = torch.from_numpy(bits.view(np.int16)).view(torch.bfloat16)
+    return y
+
+
+def cl_to_u8(x, C, out=None):
+    """vcof_cl_to_u8 through the library's HOST evaluation of the kernel's own per-element function."""
+    import numpy as np
+    from videocof_b200 import _lib
+    bits = np.ascontiguousarray(x[..., :C].contiguous().view(torch.int16).numpy()).view(np.uint16)
+    res = np.empty(bits.shape, dtype=np.uint8)
+    _lib.call("vcof_debug_frame_u8_host", bits.ctypes.data, res.ctypes.data, bits.size)
+    res = torch.from_numpy(res)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
 def softmax_rows(s, scale, out=None):
     return torch.softmax(s.float() * scale, dim=-1).to(torch.bfloat16)
 
@@ -195,6 +222,7 @@ def install_t5(monkeypatch):
 
 def install(monkeypatch):
     from videocof_b200 import ops, vae
-    for name in ("gemm", "conv_igemm", "conv_lines", "rms_silu_cl", "nchw_to_cl", "cl_to_nchw", "softmax_rows"):
+    for name in ("gemm", "conv_igemm", "conv_lines", "rms_silu_cl", "nchw_to_cl", "cl_to_nchw", "softmax_rows",
+                 "u8_to_cl", "cl_to_u8"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(vae.AutoencoderKLWan_, "_check", lambda self, x: None)

@@ -369,6 +369,40 @@ def cl_to_nchw(x, C, sub=None, mul=None):
     return y
 
 
+def u8_to_cl(frames, Cp):
+    """Byte frames uint8 [T, H, W, C] -> channels-last bf16 [T, H, W, Cp] = bf16(fp32(u) * fp32(2/255) - 1), channels
+    >= C zero: load_video_frames' scaling (reference fast_infer.py:86-88) + the cast to the VAE dtype
+    (pipeline_wan.py:397) + the layout pass of the encoder's first layer, bit-exact."""
+    _chk(frames, torch.uint8, "u8_to_cl.frames", 4)
+    if not frames.is_contiguous():
+        raise _lib.VcofError("u8_to_cl.frames must be contiguous")
+    T, H, W, C = frames.shape
+    if Cp < C:
+        raise _lib.VcofError(f"u8_to_cl: Cp={Cp} < C={C}")
+    y = torch.empty((T, H, W, Cp), dtype=torch.bfloat16, device=frames.device)
+    _call("vcof_u8_to_cl", frames.data_ptr(), y.data_ptr(), T * H * W, C, Cp, _stream())
+    return y
+
+
+def cl_to_u8(x, C, out=None):
+    """Decoder output bf16 [T, H, W, ld >= C] -> byte frames uint8 [T, H, W, C] =
+    trunc(255 * clamp(bf16(bf16(x / 2) + 0.5), 0, 1)): decode_latents (pipeline_wan.py:425-427) + save_videos_grid's
+    uint8 conversion (utils/utils.py:66), bit-exact."""
+    _chk(x, torch.bfloat16, "cl_to_u8.x", 4)
+    T, H, W, ld = x.shape
+    dense = (H * W * ld, W * ld, ld, 1)
+    if any(x.shape[i] > 1 and x.stride(i) != dense[i] for i in range(4)):
+        raise _lib.VcofError("cl_to_u8.x must be a dense channels-last tensor")
+    if out is None:
+        out = torch.empty((T, H, W, C), dtype=torch.uint8, device=x.device)
+    else:
+        _chk(out, torch.uint8, "cl_to_u8.out", 4)
+        if tuple(out.shape) != (T, H, W, C) or not out.is_contiguous():
+            raise _lib.VcofError("cl_to_u8.out must be a contiguous uint8 [T, H, W, C]")
+    _call("vcof_cl_to_u8", x.data_ptr(), ld, out.data_ptr(), T * H * W, C, _stream())
+    return out
+
+
 def softmax_rows(s, scale, out=None):
     """bf16 softmax(s * scale) over the last dim of fp32 s [rows, n]."""
     _chk(s, torch.float32, "softmax.s", 2)

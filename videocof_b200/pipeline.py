@@ -132,6 +132,12 @@ class WanPipeline:
 
     # ---- latents (:343-419) ------------------------------------------------------------------------------------
     def _encode_source(self, video, dtype, device):
+        if video.dtype == torch.uint8:
+            # byte frames [B, T, H, W, 3] (videocof_b200.video_io.load_video_frames(..., as_uint8=True)): one quarter of
+            # the fp32 bytes go over PCIe; the [-1, 1] scaling and the cast to bf16 run inside the VAE's layout kernel
+            video = video.to(device=device, non_blocking=True)
+            lat = [self.vae.encode_frames(video[i:i + 1])[0].mode() for i in range(video.shape[0])]
+            return torch.cat(lat, dim=0).to(dtype)
         video = video.to(device=device, dtype=dtype)
         lat = [self.vae.encode(video[i:i + 1])[0].mode() for i in range(video.shape[0])]
         return torch.cat(lat, dim=0)
@@ -162,6 +168,11 @@ class WanPipeline:
         frames = self.vae.decode(latents.to(self.vae.dtype)).sample
         frames = (frames / 2 + 0.5).clamp(0, 1)
         return frames.cpu().float().numpy()
+
+    def decode_frames(self, latents):
+        """decode_latents + the uint8 conversion of save_videos_grid (utils/utils.py:66) on the device: uint8
+        [B, T, H, W, 3] numpy on the host, bit-identical to what the reference writes to the video file."""
+        return self.vae.decode_frames(latents.to(self.vae.dtype)).cpu().numpy()
 
     # ---- __call__ (:518-799) -----------------------------------------------------------------------------------
     @torch.no_grad()
@@ -240,20 +251,22 @@ class WanPipeline:
 
         ground_video = edit_video = None
         out_video = latents
-        if output_type == "numpy":
+        if output_type in ("numpy", "uint8"):
+            # "uint8" (not in the reference): byte frames [B, T, H, W, 3] converted on the device; time is axis 1 there
+            decode, t_axis = (self.decode_latents, 2) if output_type == "numpy" else (self.decode_frames, 1)
             if cot:
                 g0, g1 = condition_count, condition_count + ground_latent_count
                 parts = []
                 if g1 > g0 and g0 < latents.shape[2]:
-                    ground_video = self.decode_latents(latents[:, :, g0:g1])
+                    ground_video = decode(latents[:, :, g0:g1])
                     parts.append(ground_video)
                 if g1 < latents.shape[2]:
-                    edit_video = self.decode_latents(latents[:, :, g1:])
+                    edit_video = decode(latents[:, :, g1:])
                     parts.append(edit_video)
-                out_video = np.concatenate(parts, axis=2)
+                out_video = np.concatenate(parts, axis=t_axis)
             else:
                 if condition_count < latents.shape[2]:
-                    edit_video = self.decode_latents(latents[:, :, condition_count:])
+                    edit_video = decode(latents[:, :, condition_count:])
                 out_video = edit_video
         self.maybe_free_model_hooks()
         if not return_dict:

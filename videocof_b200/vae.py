@@ -666,7 +666,9 @@ class AutoencoderKLWan_(nn.Module):
         return x, x_act
 
     def encode(self, x, scale, shard=None):
-        """x [1, 3, T, H, W] -> [1, 2*z, f, H/8, W/8] = cat(normalised mu, logvar) (:520-548).
+        """x [1, 3, T, H, W] -> [1, 2*z, f, H/8, W/8] = cat(normalised mu, logvar) (:520-548).  x may also be the byte
+        frames uint8 [1, T, H, W, 3] of the clip: the [-1, 1] scaling of load_video_frames (fast_infer.py:86-88) and
+        the cast to bf16 (pipeline_wan.py:397) then happen in the layout kernel (bit-identical input to the first conv).
 
         shard: optional TimeShard — rank r encodes the video frames of its latent-frame range (frame 0 alone, then 4
         per latent: the reference's own chunk boundaries) with 2-frame halos; the latents are all-gathered."""
@@ -674,21 +676,26 @@ class AutoencoderKLWan_(nn.Module):
         self._check(x)
         if x.shape[0] != 1:
             raise VcofError("encode expects batch 1 (the reference loops over the batch, :647-653)")
-        if (x.shape[2] - 1) % 4 != 0 or x.shape[3] % 8 or x.shape[4] % 8:
+        as_bytes = x.dtype == torch.uint8
+        if as_bytes and (x.dim() != 5 or x.shape[4] != 3):
+            raise VcofError(f"byte frames must be uint8 [1, T, H, W, 3], got {tuple(x.shape)}")
+        T, H, W = (x.shape[1], x.shape[2], x.shape[3]) if as_bytes else (x.shape[2], x.shape[3], x.shape[4])
+        if (T - 1) % 4 != 0 or H % 8 or W % 8:
             raise VcofError("video must have 1+4k frames and H, W multiples of 8")
         enc = self.encoder
-        T = x.shape[2]
         f = (T - 1) // 4 + 1
         sharded = shard is not None and shard.world > 1 and f >= 2 * shard.world
-        xv = x[0].to(torch.bfloat16)
+        t0, t1 = 0, T
         if sharded:
             base, extra = divmod(f, shard.world)
             sizes = [base + (1 if r < extra else 0) for r in range(shard.world)]
             a0 = sum(sizes[:shard.rank])
             b0 = a0 + sizes[shard.rank]
             t0, t1 = (0 if a0 == 0 else 4 * a0 - 3), 4 * b0 - 3
-            xv = xv[:, t0:t1]
-        h = ops.nchw_to_cl(xv.contiguous(), 32)
+        if as_bytes:
+            h = ops.u8_to_cl(x[0, t0:t1].contiguous(), 32)
+        else:
+            h = ops.nchw_to_cl(x[0].to(torch.bfloat16)[:, t0:t1].contiguous(), 32)
         if sharded:
             _SHARD = shard
             own = _alloc(*h.shape, h.device)
@@ -714,9 +721,12 @@ class AutoencoderKLWan_(nn.Module):
             out = shard.gather_frames(out, sizes)
         return out[None]
 
-    def decode(self, z, scale, shard=None):
+    def decode(self, z, scale, shard=None, as_bytes=False):
         """z [1, 16, f, h, w] (normalised) -> [1, 3, 4(f-1)+1, 8h, 8w] (:550-575); clamp is applied by the caller
-        in the reference (:669) and fused into the last convolution here.
+        in the reference (:669) and fused into the last convolution here.  as_bytes: return the byte frames uint8
+        [1, T, 8h, 8w, 3] the reference's host chain would make of that output — decode_latents' bf16
+        (x / 2 + 0.5).clamp(0, 1) -> fp32 (pipeline_wan.py:425-427), save_videos_grid's (x * 255).astype(uint8)
+        (utils/utils.py:66) — bit-exactly, converted on the device.
 
         shard: optional TimeShard — the latent frames are split into contiguous per-rank ranges, every causal
         convolution exchanges a 2-frame halo with the left neighbour, and the decoded frames are all-gathered."""
@@ -748,9 +758,15 @@ class AutoencoderKLWan_(nn.Module):
             h = conv_causal(a_, dec.head[2], clamp=1.0, n_store=3)  # [T, H, W, 8] (3 real channels)
         finally:
             _SHARD = None
-        out = ops.cl_to_nchw(h, 3)                                   # [3, T_r, H, W]
         if sharded:
             counts = [4 * n - (3 if r == 0 else 0) for r, n in enumerate(sizes)]
+        if as_bytes:
+            out = ops.cl_to_u8(h, 3)                                 # [T_r, H, W, 3]
+            if sharded:
+                out = shard.gather_frames(out[None], counts)[0]
+            return out[None]
+        out = ops.cl_to_nchw(h, 3)                                   # [3, T_r, H, W]
+        if sharded:
             out = shard.gather_frames(out, counts)
         return out[None]
 
@@ -830,6 +846,19 @@ class AutoencoderKLWan(nn.Module):
     def encode(self, x, return_dict=True):
         posterior = DiagonalGaussianDistribution(self._encode(x))
         return AutoencoderKLOutput(latent_dist=posterior) if return_dict else (posterior,)
+
+    def encode_frames(self, frames, return_dict=True):
+        """`encode` for byte frames uint8 [B, T, H, W, 3] (what load_video_frames stacks before its float scaling,
+        fast_infer.py:86): a quarter of the fp32 bytes cross PCIe and the scaling runs inside the layout kernel."""
+        if frames.dtype != torch.uint8:
+            raise VcofError(f"encode_frames expects uint8 frames, got {frames.dtype}")
+        return self.encode(frames, return_dict=return_dict)
+
+    def decode_frames(self, z):
+        """z [B, 16, f, h, w] -> byte frames uint8 [B, T, H, W, 3] on the device, bit-identical to the reference's
+        decode -> decode_latents -> save_videos_grid chain (pipeline_wan.py:424-427, utils/utils.py:66)."""
+        shard = getattr(self, "_shard", None)
+        return torch.cat([self.model.decode(u.unsqueeze(0), self.scale, shard=shard, as_bytes=True) for u in z], dim=0)
 
     def enable_temporal_sharding(self, group=None):
         """Encode / decode with the frames sharded over the ranks of `group` (default WORLD): 2-frame halo exchange
