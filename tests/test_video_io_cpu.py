@@ -224,3 +224,16 @@ def test_vae_byte_frames_match_float_path(vae_model, monkeypatch):
         vae_model.encode_frames(video)                                       # float clip: wrong entry point
     with pytest.raises(VcofError):
         vae_model.encode_frames(frames[..., :2])                             # not RGB
+
+
+def test_overlay_utils_exports():
+    """`from videox_fun.utils.utils import filter_kwargs, save_videos_grid` (fast_infer.py:37) resolves through the
+    overlay: the writer takes bytes, filter_kwargs behaves like the reference's (utils/utils.py:17-21)."""
+    import videox_fun.utils.utils as m
+    from videocof_b200 import video_io
+    assert m.save_videos_grid is video_io.save_videos_grid
+
+    class K:
+        def __init__(self, a, b=2):
+            pass
+    assert m.filter_kwargs(K, {"a": 1, "c": 3, "self": 0}) == {"a": 1}
