@@ -17,8 +17,14 @@ def gemm(a, w, bias=None, epilogue="bias", out=None, gate=None, narrow=False):
         r = acc.to(torch.bfloat16).float()
         out.copy_((out.float() * r if epilogue == "mul" else out.float() + r).to(torch.bfloat16))
         return out
+    if epilogue == "bias_gate_res":       # in place on the fp32 residual: out += gate[n] * bf16(acc + bias)
+        r = acc.to(torch.bfloat16).float()
+        out += r if gate is None else gate.float() * r
+        return out
     if epilogue == "raw_f32":
         res = acc
+    elif epilogue == "bias_f32":
+        res = acc.to(torch.bfloat16).float()
     elif epilogue == "bias":
         res = acc.to(torch.bfloat16)
     elif epilogue == "bias_gelu":
@@ -211,6 +217,115 @@ def t5_attention(q, k, v, bias_rel, B, L, heads, key_mask=None, out=None):
         out.copy_(res)
         return out
     return res
+
+
+# ---- DiT entry points (include/vcof.h: vcof_attn_fwd, vcof_ln_modulate, vcof_rmsnorm_rope[_blocked], vcof_copy_blocked,
+# ---- vcof_patchify, vcof_unpatchify, vcof_linear_f32) ------------------------------------------------------------
+
+def attention(q, k, v, heads, kv_len=None, scale=None, out=None, v_transposed=False):
+    """softmax(q k^T * scale) v per head over keys [0, kv_len); fp32 scores, bf16 output."""
+    Lq, C = q.shape
+    d = C // heads
+    Lk = k.shape[0]
+    kv_len = Lk if kv_len is None else kv_len
+    scale = d ** -0.5 if scale is None else scale
+    qh = q.float().view(Lq, heads, d).transpose(0, 1)
+    kh = k.float()[:kv_len].view(kv_len, heads, d).transpose(0, 1)
+    vf = v.float().t() if v_transposed else v.float()
+    vh = vf[:kv_len].view(kv_len, heads, d).transpose(0, 1)
+    p = torch.softmax(qh @ kh.transpose(1, 2) * scale, dim=-1)
+    o = (p @ vh).transpose(0, 1).reshape(Lq, C).to(torch.bfloat16)
+    if out is not None:
+        out.copy_(o)
+        return out
+    return o
+
+
+def ln_modulate(x, ln_w=None, ln_b=None, shift=None, scale=None, eps=1e-6, out=None):
+    y = torch.nn.functional.layer_norm(x.float(), (x.shape[1],), ln_w, ln_b, eps)
+    if scale is not None:
+        y = y * (1 + scale)
+    if shift is not None:
+        y = y + shift
+    y = y.to(torch.bfloat16)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def _rmsnorm_rope(x, weight, eps, head_dim, rope):
+    """y = bf16(bf16(x * bf16(rsqrt(mean(x^2) + eps))) * w), then the 3-axis rotation of interleaved pairs in fp32 and
+    one more rounding; rows beyond the F*H*W grid are normalised but not rotated."""
+    L, C = x.shape
+    xf = x.float()
+    inv = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps).to(torch.bfloat16).float()
+    y = ((xf * inv).to(torch.bfloat16).float() * weight.float()).to(torch.bfloat16)
+    if rope is None:
+        return y
+    half = head_dim // 2
+    g = torch.arange(L) + rope.row_offset
+    inside = g < rope.F * rope.H * rope.W
+    gc = g.clamp(max=rope.F * rope.H * rope.W - 1)
+    fi, hi, wi = gc // (rope.H * rope.W), (gc // rope.W) % rope.H, gc % rope.W
+    pos = torch.empty(L, half, dtype=torch.long)
+    pos[:, :rope.n_t] = rope.tpos.long()[fi][:, None]
+    pos[:, rope.n_t:rope.n_t + rope.n_h] = hi[:, None]
+    pos[:, rope.n_t + rope.n_h:] = wi[:, None]
+    cs = rope.table[pos, torch.arange(half)[None, :]]                    # [L, half, 2]
+    cos, sin = cs[..., 0][:, None, :], cs[..., 1][:, None, :]
+    yf = y.float().view(L, C // head_dim, half, 2)
+    x0, x1 = yf[..., 0], yf[..., 1]
+    rot = torch.stack([x0 * cos - x1 * sin, x0 * sin + x1 * cos], dim=-1).view(L, C).to(torch.bfloat16)
+    return torch.where(inside[:, None], rot, y)
+
+
+def rmsnorm_rope_(x, weight, eps, head_dim, rope=None, out_blocked=None):
+    y = _rmsnorm_rope(x, weight, eps, head_dim, rope)
+    if out_blocked is not None:
+        return copy_blocked(y, out_blocked, True)
+    x.copy_(y)
+    return x
+
+
+def copy_blocked(rowmajor, blocked, to_blocked):
+    P, rows, cp = blocked.shape
+    if to_blocked:
+        blocked.copy_(rowmajor.view(rows, P, cp).transpose(0, 1))
+        return blocked
+    rowmajor.view(rows, P, cp).copy_(blocked.transpose(0, 1))
+    return rowmajor
+
+
+def patchify(x):
+    Cin, F, H, W = x.shape
+    return x.view(Cin, F, H // 2, 2, W // 2, 2).permute(1, 2, 4, 0, 3, 5).reshape(F * (H // 2) * (W // 2), Cin * 4)
+
+
+def unpatchify(y, Cout, F, H, W, out=None):
+    L = F * (H // 2) * (W // 2)
+    res = y[:L].reshape(F, H // 2, W // 2, 2, 2, Cout).permute(5, 0, 1, 3, 2, 4).reshape(Cout, F, H, W).contiguous()
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def linear_f32(x, w, bias=None, act_in=False, act_out=False):
+    v = torch.nn.functional.silu(x) if act_in else x
+    v = v @ w.float().t()
+    if bias is not None:
+        v = v + bias.float()
+    return torch.nn.functional.silu(v) if act_out else v
+
+
+def install_dit(monkeypatch):
+    """Replace the libvcof entry points the DiT uses (videocof_b200/dit.py, dist.py) by the statements above."""
+    from videocof_b200 import dit, ops
+    for name in ("gemm", "attention", "ln_modulate", "rmsnorm_rope_", "copy_blocked", "patchify", "unpatchify",
+                 "linear_f32"):
+        monkeypatch.setattr(ops, name, globals()[name])
+    monkeypatch.setattr(dit.WanTransformer3DModel, "_check_ready", lambda self, x: None)
 
 
 def install_t5(monkeypatch):
