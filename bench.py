@@ -292,13 +292,18 @@ def run_vcof(args):
             vae.enable_temporal_sharding()          # the DiT is already sequence-parallel (see above)
         src_frames = 4 * fs - 3                                   # fs latent frames of source video
         H, W = lat[2] * 8, lat[3] * 8
-        video_host = (torch.rand(1, 3, src_frames, H, W, generator=g) * 2 - 1).to(torch.bfloat16).pin_memory()
+        if args.pipeline_bytes:     # byte frames in and out (videocof_b200/video_io.py)
+            video_host = torch.randint(0, 256, (1, src_frames, H, W, 3), generator=g, dtype=torch.uint8).pin_memory()
+        else:
+            video_host = (torch.rand(1, 3, src_frames, H, W, generator=g) * 2 - 1).to(torch.bfloat16).pin_memory()
         gen = torch.Generator(device="cpu").manual_seed(4)
+        t_axis = 1 if args.pipeline_bytes else 2
 
         def run_pipe():
             return pipe(video=video_host, prompt_embeds=[ctx_host.to(dev)], height=H, width=W,
                         source_frames=src_frames, reasoning_frames=4, num_inference_steps=4, guidance_scale=1.0,
-                        shift=3, repeat_rope=True, cot=True, generator=gen)
+                        shift=3, repeat_rope=True, cot=True, generator=gen,
+                        output_type="uint8" if args.pipeline_bytes else "numpy")
 
         run_pipe()                                                # warm-up (allocator, weight packs)
         barrier()
@@ -306,11 +311,14 @@ def run_vcof(args):
         out = run_pipe()
         barrier()
         dt = time.perf_counter() - t0
-        n_edit = int(out.edit_videos.shape[2])
+        n_edit = int(out.edit_videos.shape[t_axis])
         pipe_stats = {"seconds": dt, "frames_per_sec": n_edit / dt, "edit_frames": n_edit,
-                      "ground_frames": int(out.ground_videos.shape[2]), "source_frames": src_frames,
-                      "what": "WanPipeline.__call__: VAE encode(source, host bf16) + 4 DiT steps + VAE decode(ground) + "
-                              "VAE decode(edit) -> fp32 numpy frames on the host; random-init weights"
+                      "ground_frames": int(out.ground_videos.shape[t_axis]), "source_frames": src_frames,
+                      "what": ("WanPipeline.__call__: VAE encode(source, host uint8 frames) + 4 DiT steps + VAE "
+                               "decode(ground) + VAE decode(edit) -> uint8 frames on the host; random-init weights"
+                               if args.pipeline_bytes else
+                               "WanPipeline.__call__: VAE encode(source, host bf16) + 4 DiT steps + VAE decode(ground) + "
+                               "VAE decode(edit) -> fp32 numpy frames on the host; random-init weights")
                               + ("; DiT token-sharded, VAE frame-sharded with halos" if world > 1 else "")}
         del vae, pipe, out
 
@@ -390,6 +398,9 @@ def main():
     ap.add_argument("--no-pipeline", action="store_true", help="skip the WanPipeline (VAE + 4 steps) end-to-end leg")
     ap.add_argument("--pipeline", action="store_true",
                     help="also run the WanPipeline leg at N > 1 (DiT sequence-parallel, VAE frame-sharded)")
+    ap.add_argument("--pipeline-bytes", action="store_true",
+                    help="WanPipeline leg with uint8 frames in and out (conversions on the device) instead of bf16 in / "
+                         "fp32 out")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -1,6 +1,7 @@
 // selftest_core.cu — stand-alone parity check of the two tensor-core kernels of the denoising step over the C ABI
 // (no Python): vcof_gemm_bf16 (bias / GELU / gated fp32 residual / fp32 store epilogues) and vcof_attn_fwd
 // (head_dim 128, ragged lengths, kv_len < Lk, V^T input) against double-precision CPU restatements in this file.
+// `frames`: the byte conversions vcof_u8_to_cl / vcof_cl_to_u8 against the library's host evaluation, bit-exact.
 // Meant for kernel work: `VCOF_GEMM_2CTA=1 tests/native/selftest_core gemm`, `VCOF_ATTN_EMU=2 … attn` validate a
 // variant in seconds of GPU time.  The Python suite (tests/test_kernels_gpu.py) stays the reference gate.
 #include <cuda_bf16.h>
@@ -131,6 +132,67 @@ static void case_attn(int Lq, int Lk, int kv, int heads, int vt) {
   cudaFree(dq); cudaFree(dk); cudaFree(dv); cudaFree(dout);
 }
 
+// Frame bytes (vcof_u8_to_cl / vcof_cl_to_u8): the device kernels against the library's HOST evaluation of the same
+// per-element functions (pinned exhaustively to the executed reference by tests/test_video_io_cpu.py).  Bit-exact.
+static void report_bytes(const char* name, const char* shape, size_t mismatches, int rc) {
+  const cudaError_t e = cudaDeviceSynchronize();
+  const bool ok = rc == 0 && e == cudaSuccess && mismatches == 0;
+  if (!ok) ++g_fail;
+  printf("{\"case\": \"%s\", \"shape\": \"%s\", \"rc\": %d, \"cuda\": %d, \"mismatches\": %zu, \"ok\": %s%s%s%s}\n", name,
+         shape, rc, (int)e, mismatches, ok ? "true" : "false", rc ? ", \"error\": \"" : "", rc ? vcof_last_error() : "",
+         rc ? "\"" : "");
+  fflush(stdout);
+}
+
+static void case_frames_out(long long npos, int C, int ld, int byte_offset) {
+  // every 16-bit pattern cycles through the real channels; the padding channels hold junk
+  std::vector<unsigned short> x((size_t)npos * ld + 8), xr((size_t)npos * C);
+  unsigned short pat = 0;
+  for (long long p = 0; p < npos; ++p)
+    for (int c = 0; c < ld; ++c) {
+      const unsigned short v = (unsigned short)(pat += 257);
+      x[(size_t)p * ld + c + byte_offset / 2] = v;
+      if (c < C) xr[(size_t)p * C + c] = v;
+    }
+  std::vector<unsigned char> ref((size_t)npos * C);
+  vcof_debug_frame_u8_host(xr.data(), ref.data(), npos * C);
+  unsigned short* dx = to_dev(x);
+  unsigned char* dout = nullptr;
+  cudaMalloc(&dout, (size_t)npos * C + 16);
+  cudaMemset(dout, 0xAB, (size_t)npos * C + 16);
+  const int rc = vcof_cl_to_u8(reinterpret_cast<char*>(dx) + byte_offset, ld, dout, npos, C, nullptr);
+  std::vector<unsigned char> got = to_host(dout, (size_t)npos * C + 16);
+  size_t bad = 0;
+  for (size_t i = 0; i < ref.size(); ++i) bad += got[i] != ref[i];
+  for (size_t i = ref.size(); i < got.size(); ++i) bad += got[i] != 0xAB;          // nothing written past the end
+  char shape[96];
+  snprintf(shape, sizeof shape, "npos=%lld C=%d ld=%d offset=%dB", npos, C, ld, byte_offset);
+  report_bytes("cl_to_u8", shape, bad, rc);
+  cudaFree(dx); cudaFree(dout);
+}
+
+static void case_frames_in(long long npos, int C, int Cp) {
+  std::vector<unsigned char> f((size_t)npos * C);
+  for (size_t i = 0; i < f.size(); ++i) f[i] = (unsigned char)(i * 37 + (i >> 8));
+  std::vector<unsigned short> conv(f.size());
+  vcof_debug_video_bf16_host(f.data(), conv.data(), (long long)f.size());
+  unsigned char* df = to_dev(f);
+  unsigned short* dy = nullptr;
+  cudaMalloc(&dy, ((size_t)npos * Cp + 8) * 2);
+  cudaMemset(dy, 0xCD, ((size_t)npos * Cp + 8) * 2);
+  const int rc = vcof_u8_to_cl(df, dy, npos, C, Cp, nullptr);
+  std::vector<unsigned short> got = to_host(dy, (size_t)npos * Cp + 8);
+  size_t bad = 0;
+  for (long long p = 0; p < npos; ++p)
+    for (int c = 0; c < Cp; ++c)
+      bad += got[(size_t)p * Cp + c] != (c < C ? conv[(size_t)p * C + c] : (unsigned short)0);
+  for (size_t i = (size_t)npos * Cp; i < got.size(); ++i) bad += got[i] != 0xCDCD;
+  char shape[96];
+  snprintf(shape, sizeof shape, "npos=%lld C=%d Cp=%d", npos, C, Cp);
+  report_bytes("u8_to_cl", shape, bad, rc);
+  cudaFree(df); cudaFree(dy);
+}
+
 int main(int argc, char** argv) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { puts("{\"error\": \"no CUDA device\"}"); return 3; }
@@ -153,6 +215,22 @@ int main(int argc, char** argv) {
     }
     case_attn(300, 333, 333, 2, 0);
     case_attn(1024, 128, 128, 40, 0);                    // 160 work items > 148 SMs: persistent CTAs walk several items
+  }
+  if (all || strcmp(argv[1], "frames") == 0) {
+    case_frames_out(65536, 3, 8, 0);          // vector path: every bf16 pattern
+    case_frames_out(1027, 3, 8, 0);           // vector path + 3-position scalar tail
+    case_frames_out(3, 3, 8, 0);              // fewer than four positions
+    case_frames_out(513, 3, 8, 8);            // rows 8 bytes off a 16-byte boundary: generic path
+    case_frames_out(70000, 3, 3, 0);          // dense RGB input
+    case_frames_out(4099, 4, 32, 0);          // generic shape
+    case_frames_out(9 * 720 * 1280, 3, 8, 0); // nine 720p frames
+    case_frames_in(1, 3, 32);
+    case_frames_in(1000, 3, 32);              // the encoder's shape (4 groups per row)
+    case_frames_in(1000, 3, 8);
+    case_frames_in(777, 8, 8);
+    case_frames_in(333, 1, 3);                // generic path
+    case_frames_in(500, 4, 12);
+    case_frames_in(9 * 720 * 1280, 3, 32);    // nine 720p frames
   }
   printf("{\"failed\": %d}\n", g_fail);
   return g_fail ? 1 : 0;

@@ -16,6 +16,10 @@ run tests/native/selftest_core
 VCOF_ATTN_SPEC=1 run tests/native/selftest_core attn
 VCOF_GEMM_2CTA=1 run tests/native/selftest_core gemm
 
+# 1b. byte-frame kernels written at the end of round 1 without GPU time left (bit-exact vs the host evaluation); the
+#     Python side of the same row: python -m pytest tests/test_widen_video_io_gpu.py -q
+run tests/native/selftest_core frames
+
 # 2. attention, C2 shape on 8 heads (1/5 of a launch: same per-SM work, 5x less box time)
 run tests/native/kbench attn 75600 75600 8 3
 VCOF_ATTN_SPEC=1 run tests/native/kbench attn 75600 75600 8 3
