@@ -57,9 +57,8 @@ static void report(const char* name, const char* shape, const std::vector<bf16>&
   if (!ok) ++g_fail;
   char line[512];
   snprintf(line, sizeof line, "{\"case\": \"%s\", \"shape\": \"%s\", \"rc\": %d, \"cuda\": %d, \"rel_fro\": %.3e, "
-           "\"tol\": %.1e, \"nan\": %s, \"ok\": %s%s%s}", name, shape, rc, (int)e, rel, tol, nan ? "true" : "false",
-           ok ? "true" : "false", rc ? ", \"error\": \"" : "", rc ? vcof_last_error() : "");
-  if (rc) strncat(line, "\"", sizeof line - strlen(line) - 1);
+           "\"tol\": %.1e, \"nan\": %s, \"ok\": %s%s%s%s}", name, shape, rc, (int)e, rel, tol, nan ? "true" : "false",
+           ok ? "true" : "false", rc ? ", \"error\": \"" : "", rc ? vcof_last_error() : "", rc ? "\"" : "");
   puts(line);
   if (g_out) { fputs(line, g_out); fputc('\n', g_out); fflush(g_out); }
 }
