@@ -19,7 +19,6 @@ travel to the GPU box) on a bounded sample of the same workload.
 """
 import argparse
 import json
-import math
 import os
 import statistics
 import subprocess

@@ -1,7 +1,6 @@
 """Host-side plumbing of videocof_b200.pipeline.WanPipeline on CPU with stub DiT / VAE modules: chain-of-frames
 latent assembly, frame-split kwargs, CFG batching, frozen source frames, split ground/edit decode
 (reference videox_fun/pipeline/pipeline_wan.py:381-428, 592-799)."""
-import numpy as np
 import torch
 
 from videocof_b200.pipeline import WanPipeline, randn_tensor

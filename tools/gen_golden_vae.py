@@ -1,6 +1,5 @@
 """Golden generators for the scheduler and the VAE (split from gen_golden.py for size)."""
 import os
-import sys
 
 import numpy as np
 import torch

@@ -20,7 +20,6 @@ and stores inputs and outputs in tests/golden/video_io.npz:
 """
 import ast
 import os
-import sys
 import tempfile
 import types
 
