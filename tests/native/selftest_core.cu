@@ -92,9 +92,15 @@ static void case_gemm(int M, int N, int K, int epi) {
   cudaFree(da); cudaFree(dw); cudaFree(db); cudaFree(dg); cudaFree(dout);
 }
 
-static void case_attn(int Lq, int Lk, int kv, int heads, int vt) {
+// grow > 0: the keys of the b-th block of 128 are scaled by (1 + grow * b), so the running row maximum jumps by far more
+// than the lazy-rescale threshold (2^8) at every key block and the rescale path of the kernel runs at each step.
+static void case_attn(int Lq, int Lk, int kv, int heads, int vt, double grow = 0.0) {
   const int C = heads * 128;
   auto q = rand_bf16((size_t)Lq * C, 1.0), k = rand_bf16((size_t)Lk * C, 1.0), v = rand_bf16((size_t)Lk * C, 1.0);
+  if (grow > 0.0)
+    for (int j = 0; j < Lk; ++j)
+      for (int c = 0; c < C; ++c)
+        k[(size_t)j * C + c] = __float2bfloat16_rn(__bfloat162float(k[(size_t)j * C + c]) * (float)(1.0 + grow * (j / 128)));
   bf16 *dq = to_dev(q), *dk = to_dev(k), *dv = nullptr, *dout = nullptr;
   long long ldv = C;
   if (vt) {                                         // V^T [C, ldv] with kv contiguous
@@ -127,7 +133,7 @@ static void case_attn(int Lq, int Lk, int kv, int heads, int vt) {
         ref[(size_t)i * C + hd * 128 + c] = acc / sum;
       }
     }
-  char shape[96]; snprintf(shape, sizeof shape, "Lq=%d Lk=%d kv=%d heads=%d vt=%d", Lq, Lk, kv, heads, vt);
+  char shape[96]; snprintf(shape, sizeof shape, "Lq=%d Lk=%d kv=%d heads=%d vt=%d grow=%g", Lq, Lk, kv, heads, vt, grow);
   report("attn", shape, got, ref, 1.5e-2, rc);
   cudaFree(dq); cudaFree(dk); cudaFree(dv); cudaFree(dout);
 }
@@ -214,6 +220,9 @@ int main(int argc, char** argv) {
       case_attn(1280, 1280, 1280, 2, vt);
     }
     case_attn(300, 333, 333, 2, 0);
+    case_attn(300, 336, 300, 2, 0);                      // last key block holds 44 keys: masking reaches the first half
+    case_attn(256, 1024, 1000, 2, 0, 6.0);               // row maximum jumps at every key block: rescale path
+    case_attn(200, 700, 700, 1, 1, 3.0);
     case_attn(1024, 128, 128, 40, 0);                    // 160 work items > 148 SMs: persistent CTAs walk several items
   }
   if (all || strcmp(argv[1], "frames") == 0) {

@@ -14,6 +14,7 @@ run() { echo "### $*" | tee -a "$OUT"; timeout 60 "$@" | tee -a "$OUT"; }
 # 1. parity gates (default build first: it must stay green)
 run tests/native/selftest_core
 VCOF_ATTN_SPEC=1 run tests/native/selftest_core attn
+VCOF_ATTN_SPEC=2 run tests/native/selftest_core attn
 VCOF_GEMM_2CTA=1 run tests/native/selftest_core gemm
 
 # 1b. byte-frame kernels written at the end of round 1 without GPU time left (bit-exact vs the host evaluation); the
@@ -23,6 +24,7 @@ run tests/native/selftest_core frames
 # 2. attention, C2 shape on 8 heads (1/5 of a launch: same per-SM work, 5x less box time)
 run tests/native/kbench attn 75600 75600 8 3
 VCOF_ATTN_SPEC=1 run tests/native/kbench attn 75600 75600 8 3
+VCOF_ATTN_SPEC=2 run tests/native/kbench attn 75600 75600 8 3
 
 # 3. GEMM, the three DiT shapes; pair kernel with the occupancy-sized grid, then a sweep of the pair count
 for shape in "75600 5120 5120 0" "75600 13824 5120 1" "75600 5120 13824 2"; do

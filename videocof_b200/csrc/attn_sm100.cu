@@ -53,6 +53,14 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Same instruction as a volatile statement: keeps its place relative to tcgen05.wait::ld (SPEC == 2 wants a batch of
+// exponentials issued BEFORE the wait for the second half of the score load).
+__device__ __forceinline__ float ex2_ordered(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max rel.
 // error 7.5e-5 << bf16 P precision).  MUFU.EX2 runs at 16/clk/SM, i.e. exactly as long as the MMAs of
 // a 128x128 tile; moving a fraction of the exponentials off the XU pipe shortens the softmax leg of the
@@ -82,7 +90,12 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // maximum of the shifted scores is folded into the loop of the first 64 exponentials (ALU pipe, hidden under MUFU)
 // and only if some row outgrew the reference by more than 2^8 — the same condition under which the default kernel
 // rescales — is the tile redone against the advanced reference.  Same arithmetic as the default path otherwise.
-template <bool V_TRANS, int EMU, bool SPLIT_S, int PSPLIT, bool SPEC = false>
+// SPEC == 2 (experimental, VCOF_ATTN_SPEC=2, not yet run on hardware): SPEC == 1 plus a split score load — the
+// first 64 columns are waited for alone, the second 64 stay in flight (tcgen05.ld is asynchronous until
+// tcgen05.wait::ld) under the first 32 of the 64 first-half exponential pairs, and their shift + maximum is folded
+// into the other 32.  The check that decides whether the tile must be redone still covers all 128 columns and still
+// precedes the first publication of P, so the arithmetic is that of SPEC == 1.
+template <bool V_TRANS, int EMU, bool SPLIT_S, int PSPLIT, int SPEC = 0>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
@@ -307,8 +320,129 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int q0 = (item % p.num_q_blocks) * 2 * kQT;
       float m_ref = -INFINITY;  // running (possibly stale) row max, raw score units
       float l = 0.f;
-      if constexpr (SPEC) {
-        static_assert(!SPEC || (EMU == 0 && !SPLIT_S && PSPLIT == 2), "SPEC builds on the default variant");
+      if constexpr (SPEC == 2) {
+        static_assert(SPEC != 2 || (EMU == 0 && !SPLIT_S && PSPLIT == 2), "SPEC builds on the default variant");
+        float mb = -INFINITY;   // running (possibly stale) row max in scaled log2 units
+        for (int j = 0; j < n_kv; ++j) {
+          uint32_t s[128];
+          mbar_wait(s_full + 8 * t, sph);
+          tc_fence_after();
+          sph ^= 1;
+          tmem_ld32(tS + 0, s + 0);
+          tmem_ld32(tS + 32, s + 32);
+          tmem_ld_wait();
+          tmem_ld32(tS + 64, s + 64);      // in flight under the first exponentials; s[64..127] must not be touched
+          tmem_ld32(tS + 96, s + 96);      // before the next tcgen05.wait::ld
+          const bool ragged = (j == n_kv - 1 && rem < kKT);
+          if (ragged) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+              if (c >= rem) s[c] = 0xff800000u;  // -inf
+          }
+          if (j == 0) {   // first tile: no reference yet, the maximum of all 128 columns has to come first
+            tmem_ld_wait();
+            if (ragged) {
+#pragma unroll
+              for (int c = 64; c < 128; ++c)
+                if (c >= rem) s[c] = 0xff800000u;
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 128; c += 4) {
+              mx0 = fmaxf(mx0, __uint_as_float(s[c]));
+              mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+              mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
+              mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+            }
+            mb = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+          }
+          const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+          const float2 nmb2 = make_float2(-mb, -mb);
+          float2 x[64];
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            x[c] = __ffma2_rn(make_float2(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1])), sc2, nmb2);
+          float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+          uint32_t pk[32];
+          float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (c == 16) {     // 32 exponential pairs (~256 clk of MUFU per warp) after the loads were issued
+              tmem_ld_wait();
+              if (j > 0 && ragged) {
+#pragma unroll
+                for (int e = 64; e < 128; ++e)
+                  if (e >= rem) s[e] = 0xff800000u;
+              }
+            }
+            float2 pr;
+            pr.x = c < 16 ? ex2_ordered(x[c].x) : ex2(x[c].x);
+            pr.y = c < 16 ? ex2_ordered(x[c].y) : ex2(x[c].y);
+            if (c & 1) acc1 = __fadd2_rn(acc1, pr); else acc0 = __fadd2_rn(acc0, pr);
+            pk[c] = pack_bf16x2(pr.x, pr.y);
+            mxa = fmaxf(fmaxf(mxa, x[c].x), x[c].y);
+            if (c >= 16) {     // shift + maximum of the second half, two pairs per iteration, hidden under MUFU
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const int e = 32 + 2 * (c - 16) + q;
+                x[e] = __ffma2_rn(make_float2(__uint_as_float(s[2 * e]), __uint_as_float(s[2 * e + 1])), sc2, nmb2);
+                mxb = fmaxf(fmaxf(mxb, x[e].x), x[e].y);
+              }
+            }
+          }
+          const float mxx = fmaxf(mxa, mxb);
+          if (j > 0 && __any_sync(0xffffffffu, mxx > kRescaleThresh)) {
+            // rare: as in SPEC == 1 — advance the reference by d (per row), rescale O_t and l, redo the first half
+            const float d = fmaxf(mxx, 0.f);
+            const float alpha = ex2(-d);
+            l *= alpha;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st32(tO + c * 32, o);
+            }
+            tmem_st_wait();
+            mb += d;
+            const float2 nd2 = make_float2(-d, -d);
+#pragma unroll
+            for (int c = 0; c < 64; ++c) x[c] = __fadd2_rn(x[c], nd2);
+            acc0 = make_float2(0.f, 0.f);
+            acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              float2 pr;
+              pr.x = ex2(x[c].x);
+              pr.y = ex2(x[c].y);
+              if (c & 1) acc1 = __fadd2_rn(acc1, pr); else acc0 = __fadd2_rn(acc0, pr);
+              pk[c] = pack_bf16x2(pr.x, pr.y);
+            }
+          }
+          tmem_st32(tS, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_part + 8 * (0 * 2 + t));
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float2 pr;
+            pr.x = ex2(x[32 + c].x);
+            pr.y = ex2(x[32 + c].y);
+            if (c & 1) acc1 = __fadd2_rn(acc1, pr); else acc0 = __fadd2_rn(acc0, pr);
+            pk[c] = pack_bf16x2(pr.x, pr.y);
+          }
+          tmem_st32(tS + 32, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_part + 8 * (1 * 2 + t));
+          l += (acc0.x + acc1.x) + (acc0.y + acc1.y);
+        }
+      } else if constexpr (SPEC == 1) {
+        static_assert(SPEC != 1 || (EMU == 0 && !SPLIT_S && PSPLIT == 2), "SPEC builds on the default variant");
         float mb = -INFINITY;   // running (possibly stale) row max in scaled log2 units
         for (int j = 0; j < n_kv; ++j) {
           uint32_t s[128];
@@ -586,13 +720,15 @@ extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long l
     const char* q = getenv("VCOF_ATTN_PSPLIT");
     psplit = (q && atoi(q) == 4) ? 4 : 2;
   }
-  static const bool spec = [] {
+  static const int spec = [] {
     const char* e = getenv("VCOF_ATTN_SPEC");
-    return e != nullptr && e[0] == '1';
+    return e == nullptr ? 0 : (e[0] == '1' ? 1 : (e[0] == '2' ? 2 : 0));
   }();
   int lrc = 0;
-  if (spec && emu == 0 && !split_s && psplit == 2) {   // experimental: row maximum off the critical path
-    lrc = v_transposed ? launch(attn_fwd_kernel<true, 0, false, 2, true>) : launch(attn_fwd_kernel<false, 0, false, 2, true>);
+  if (spec == 1 && emu == 0 && !split_s && psplit == 2) {   // experimental: row maximum off the critical path
+    lrc = v_transposed ? launch(attn_fwd_kernel<true, 0, false, 2, 1>) : launch(attn_fwd_kernel<false, 0, false, 2, 1>);
+  } else if (spec == 2 && emu == 0 && !split_s && psplit == 2) {   // ... and half of the score load under the exps
+    lrc = v_transposed ? launch(attn_fwd_kernel<true, 0, false, 2, 2>) : launch(attn_fwd_kernel<false, 0, false, 2, 2>);
   } else if (emu == 3 || split_s) {            // experimental variants, natural-V layout only
     VCOF_REQUIRE(!v_transposed, "vcof_attn_fwd: tuning variants support the natural V layout only");
     if (emu == 3) lrc = launch(attn_fwd_kernel<false, 3, false, 2>);
