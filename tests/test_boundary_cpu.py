@@ -80,3 +80,48 @@ def test_product_never_imports_oracle():
                     if re.search(r"^\s*(from|import)\s+oracle\b", s, flags=re.M):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_c_abi_rejects_bad_arguments_with_a_message():
+    """Error behaviour of the C ABI (include/vcof.h): a malformed call returns a negative code BEFORE anything is
+    launched and leaves a message naming the entry point in vcof_last_error(); the Python shim turns that into
+    VcofError (the reference's style is an assert / exception at the call site, e.g. attention_utils.py:72-73).
+    Argument validation touches no device, so this runs without a GPU."""
+    from videocof_b200 import _lib
+    lib = _lib.load()
+    buf = (ctypes.c_char * 4096)()
+    p = ctypes.addressof(buf)
+    p = (p + 255) // 256 * 256                      # an aligned host address: never dereferenced by validation
+    bad = [
+        ("vcof_attn_fwd", (p, 64, p, 64, p, 64, p, 64, 128, 128, 128, 1, 64, 0.125, 0, None), "head_dim"),
+        ("vcof_attn_fwd", (p, 128, p, 128, p, 128, p, 128, 128, 128, 200, 1, 128, 0.09, 0, None), "kv_len"),
+        ("vcof_attn_fwd", (p, 128, p, 128, p, 128, p, 128, 0, 128, 128, 1, 128, 0.09, 0, None), "empty"),
+        ("vcof_gemm_bf16", (p, 64, p, 64, None, None, p, 64, 0, 64, 64, 0, None), "empty"),
+        ("vcof_gemm_bf16", (p, 60, p, 64, None, None, p, 64, 128, 64, 64, 0, None), "vcof_gemm_bf16"),
+        ("vcof_gemm_bf16", (p, 64, p, 64, None, None, p, 300, 128, 300, 64, 0, None), "ldo"),
+        ("vcof_gemm_bf16", (p, 64, p, 64, p, None, p, 64, 128, 64, 64, 5, None), "vcof_gemm_bf16"),
+        ("vcof_ln_modulate", (p, 64, None, None, None, None, p, 64, 0, 64, 1e-6, None), "empty"),
+        ("vcof_ln_modulate", (p, 66, None, None, None, None, p, 66, 4, 66, 1e-6, None), "vcof_ln_modulate"),
+        ("vcof_rmsnorm_rope", (p, 256, p, 1e-6, 4, 256, 100, None, None, 1, 1, 1, 0, 0, 0, None), "head_dim"),
+        ("vcof_copy_blocked", (p, 64, p, 64, 4, 60, 8, 1, None), "vcof_copy_blocked"),
+        ("vcof_patchify", (p, p, 16, 2, 5, 8, None), "vcof_patchify"),
+        ("vcof_unpatchify", (p, 64, p, 16, 2, 8, 7, None), "vcof_unpatchify"),
+        ("vcof_linear_f32", (p, p, None, p, 1, 8, 12, 0, 0, None), "vcof_linear_f32"),
+        ("vcof_cl_to_u8", (p, 8, p, 0, 3, None), "vcof_cl_to_u8"),
+        ("vcof_cl_to_u8", (p, 2, p, 16, 3, None), "vcof_cl_to_u8"),
+        ("vcof_cl_to_u8", (None, 8, p, 16, 3, None), "null"),
+        ("vcof_u8_to_cl", (p, p, 16, 3, 2, None), "vcof_u8_to_cl"),
+        ("vcof_u8_to_cl", (p, None, 16, 3, 32, None), "null"),
+        ("vcof_embed_rows", (p, p, 64, 100, p, 64, 0, 64, None), "empty"),
+        ("vcof_embed_rows", (p, p, 64, 100, p, 64, 5, 60, None), "multiples of 8"),
+        ("vcof_t5_rmsnorm", (p, 64, p, p, 64, 4, 60, 1e-6, None), "vcof_t5_rmsnorm"),
+        ("vcof_t5_attn", (p, 64, p, 64, p, 64, p, 64, p, 1023, None, 1, 513, 1, 64, None), "512"),
+        ("vcof_t5_attn", (p, 64, p, 64, p, 64, p, 64, None, 0, None, 1, 16, 1, 64, None), "bias"),
+    ]
+    for name, args, needle in bad:
+        rc = getattr(lib, name)(*args)
+        msg = lib.vcof_last_error().decode()
+        assert rc < 0, (name, args, rc)
+        assert needle in msg and name in msg, (name, needle, msg)
+        with pytest.raises(_lib.VcofError, match=name):
+            _lib.call(name, *args)
