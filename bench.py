@@ -154,12 +154,25 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, 1),
+            "config": workload_config(args.workload, args.gpus),     # the libvcof arm's config, verbatim (tier rule 4)
             "cpu_baseline": {"value": v, "unit": "steps/s", "cores": last["cores"], "kind": "port",
                              "sample": last["sample"]},
             "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
+
+
+def l2_note(cfg_kw, rows):
+    """Timing rule: inputs larger than L2 or a flush between iterations — say which.  Per layer and GPU the step streams
+    the fp32 residual, four bf16 [rows, C] activations, the bf16 FFN hidden and the layer's weights."""
+    C, F = cfg_kw["dim"], cfg_kw["ffn_dim"]
+    act = rows * (C * 4 + 4 * C * 2 + F * 2)
+    wts = (8 * C * C + 2 * C * F) * 2
+    if act + wts > 4 * 126e6:
+        return (f"working set per layer ({act / 1e9:.2f} GB activations + {wts / 1e9:.2f} GB weights) >> 126 MB L2; "
+                "no flush needed")
+    return (f"working set per layer ({(act + wts) / 1e6:.0f} MB) is not >> the 126 MB L2 and no flush is done: "
+            "debug workload, not a valid bench configuration")
 
 
 def workload_config(name, n_gpus):
@@ -169,7 +182,7 @@ def workload_config(name, n_gpus):
                         f"layers={cfg_kw['num_layers']}, latents {list(lat)} -> {L} tokens, chain-of-frames "
                         f"{fs}|1|{lat[1] - fs - 1}, 4-step UniPC schedule (shift 3), batch 1",
             "tokens": L, "parallelism": f"sp{n_gpus}" if n_gpus > 1 else "single",
-            "l2": "working set per layer (>=1.5 GB activations + 0.7 GB weights) >> 126 MB L2; no flush needed"}
+            "l2": l2_note(cfg_kw, L // n_gpus)}
 
 
 # ------------------------------------------------------------------------------------------------
