@@ -113,3 +113,30 @@ def test_vae_temporal_sharding_encode_matches_unsharded(world, frames, model, mo
     rel = float((got[:16].float() - ref[:16].float()).norm() / ref[:16].float().norm())
     assert rel < 3e-2, rel
     assert all(len(m) == 0 for m in mailbox[:-1])
+
+
+def test_vae_temporal_sharding_byte_frames(model, monkeypatch):
+    """Byte frames under frame sharding: each rank converts its own frame range (bytes in: its slice of the clip;
+    bytes out: [T_r, H, W, 3] gathered along time) and the result matches the un-sharded byte path."""
+    vcof_emulator.install(monkeypatch)
+    world = 2
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(1, 16, 5, 2, 3, generator=g).bfloat16()
+    frames = torch.randint(0, 256, (1, 17, 16, 16, 3), generator=g, dtype=torch.uint8)
+    with torch.no_grad():
+        ref_dec = model.decode_frames(z)[0]                                   # [T, H, W, 3]
+        ref_mu = model.model.encode(frames, model.scale)[0]
+        mailbox, outs = [[] for _ in range(world)], [None] * world
+        for r in range(world):
+            model.model.decode(z, model.scale, shard=_FakeShard(r, world, mailbox, outs), as_bytes=True)
+        got_dec = torch.cat([o[0] for o in outs], dim=0)                      # gather_frames saw [1, T_r, H, W, 3]
+        mailbox, outs = [[] for _ in range(world)], [None] * world
+        for r in range(world):
+            model.model.encode(frames, model.scale, shard=_FakeShard(r, world, mailbox, outs))
+        got_mu = torch.cat(outs, dim=1)
+    assert got_dec.dtype == torch.uint8 and got_dec.shape == ref_dec.shape == (17, 16, 24, 3)
+    # bytes differ where the emulator's differently blocked fp32 matmuls flip a bf16 rounding (see above)
+    diff = (got_dec.int() - ref_dec.int()).abs()
+    assert int(diff.max()) <= 12 and float(diff.float().mean()) < 0.5, (int(diff.max()), float(diff.float().mean()))
+    rel = float((got_mu[:16].float() - ref_mu[:16].float()).norm() / ref_mu[:16].float().norm())
+    assert got_mu.shape == ref_mu.shape and rel < 3e-2, rel
