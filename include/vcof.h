@@ -96,6 +96,27 @@ int vcof_rmsnorm_rope_blocked(const void* x, long long ldx, void* y, int cols_pe
 int vcof_copy_blocked(void* rowmajor, long long ld, void* blocked, long long block_stride, long long rows, int C,
                       int cols_per_block, int to_blocked, void* stream);
 
+/* ---- push-style head exchange (opt-in, VCOF_SP_MODE=push): the producing kernel's stores ARE the transfer --------
+ * The three entries below write into up to 16 destination slabs given as device pointers; under sequence parallelism
+ * the slabs are the other ranks' receive buffers mapped through NVLink peer memory (torch symmetric memory), so the
+ * all-to-all of the head exchange needs no collective call: it overlaps the producing kernel store by store, and a
+ * cross-GPU barrier on the stream orders it against the consumer.  New design (the reference's exchange is xfuser /
+ * yunchang's NCCL all-to-all, dist/wan_xfuser.py:98; absent package).  The pointer array itself is a HOST array. */
+
+/* vcof_rmsnorm_rope with the result scattered: block b = columns [b*C/n_blocks, (b+1)*C/n_blocks) of every row goes to
+ * the dense [L, C/n_blocks] slab block_ptrs[b]; x is not modified. */
+int vcof_rmsnorm_rope_scatter(const void* x, long long ldx, void* const* block_ptrs, int n_blocks, const void* weight,
+                              float eps, int L, int C, int head_dim, const float* rope_table, const int* tpos, int F,
+                              int H, int W, int n_t, int n_h, int row_offset, void* stream);
+
+/* Column blocks of a row-major bf16 [rows, C] matrix (pitch ld) to the slabs block_ptrs[b] ([rows, C/n_blocks]). */
+int vcof_copy_scatter(const void* rowmajor, long long ld, void* const* block_ptrs, int n_blocks, long long rows, int C,
+                      void* stream);
+
+/* Row chunks of a bf16 [n_chunks*rows, cols] matrix (pitch ld) to the slabs chunk_ptrs[c] ([rows, cols]). */
+int vcof_copy_rows_scatter(const void* src, long long ld, void* const* chunk_ptrs, int n_chunks, long long rows,
+                           int cols, void* stream);
+
 /* Patchify latents x_bf16[Cin, F, H, W] -> tokens a_bf16[F*(H/2)*(W/2), Cin*4], column order
  * (c, ph, pw) = the flattened Conv3d weight [C, Cin, 1, 2, 2].  wan_transformer3d.py:870, 879. */
 int vcof_patchify(const void* x, void* a, int Cin, int F, int H, int W, void* stream);

@@ -92,6 +92,8 @@ def test_c_abi_rejects_bad_arguments_with_a_message():
     buf = (ctypes.c_char * 4096)()
     p = ctypes.addressof(buf)
     p = (p + 255) // 256 * 256                      # an aligned host address: never dereferenced by validation
+    ptrs = (ctypes.c_void_p * 17)(*([p] * 17))      # host array of (fake) device addresses
+    odd = (ctypes.c_void_p * 2)(p, p + 8)
     bad = [
         ("vcof_attn_fwd", (p, 64, p, 64, p, 64, p, 64, 128, 128, 128, 1, 64, 0.125, 0, None), "head_dim"),
         ("vcof_attn_fwd", (p, 128, p, 128, p, 128, p, 128, 128, 128, 200, 1, 128, 0.09, 0, None), "kv_len"),
@@ -107,6 +109,15 @@ def test_c_abi_rejects_bad_arguments_with_a_message():
         ("vcof_patchify", (p, p, 16, 2, 5, 8, None), "vcof_patchify"),
         ("vcof_unpatchify", (p, 64, p, 16, 2, 8, 7, None), "vcof_unpatchify"),
         ("vcof_linear_f32", (p, p, None, p, 1, 8, 12, 0, 0, None), "vcof_linear_f32"),
+        ("vcof_rmsnorm_rope_scatter", (p, 256, None, 2, p, 1e-6, 4, 256, 128, None, None, 1, 1, 1, 0, 0, 0, None),
+         "destination pointers"),
+        ("vcof_rmsnorm_rope_scatter", (p, 256, ptrs, 17, p, 1e-6, 4, 256, 128, None, None, 1, 1, 1, 0, 0, 0, None),
+         "destination pointers"),
+        ("vcof_rmsnorm_rope_scatter", (p, 256, ptrs, 3, p, 1e-6, 4, 256, 128, None, None, 1, 1, 1, 0, 0, 0, None),
+         "blocks"),
+        ("vcof_copy_scatter", (p, 60, ptrs, 2, 4, 64, None), "vcof_copy_scatter"),
+        ("vcof_copy_scatter", (p, 64, odd, 2, 4, 64, None), "aligned"),
+        ("vcof_copy_rows_scatter", (p, 64, ptrs, 2, 0, 64, None), "vcof_copy_rows_scatter"),
         ("vcof_cl_to_u8", (p, 8, p, 0, 3, None), "vcof_cl_to_u8"),
         ("vcof_cl_to_u8", (p, 2, p, 16, 3, None), "vcof_cl_to_u8"),
         ("vcof_cl_to_u8", (None, 8, p, 16, 3, None), "null"),

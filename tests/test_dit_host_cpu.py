@@ -157,8 +157,7 @@ def _sp_worker(rank, world, port, mode, heads, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from videocof_b200 import dit, ops
-        for name in ("gemm", "attention", "ln_modulate", "rmsnorm_rope_", "copy_blocked", "patchify", "unpatchify",
-                     "linear_f32"):
+        for name in vcof_emulator.DIT_OPS:
             setattr(ops, name, getattr(vcof_emulator, name))
         dit.WanTransformer3DModel._check_ready = lambda self, x: None
         ckw, shape, n_ctx, _ = DIT_CASES["dit_tiny"]
@@ -198,3 +197,83 @@ def test_sequence_parallel_forward_matches_single_rank(world, mode, heads):
     for rank, err, shape in res:
         assert err < 2e-3, (rank, err)          # bf16 rounding flips from differently blocked host GEMMs only
         assert shape == (1, 16, 3, 10, 6)
+
+
+# ---- push exchange (symmetric memory stands in as plain tensors shared between threads) ----------------------
+
+class _ThreadSP:
+    """videocof_b200.dist.SequenceParallel for rank `rank` of `world` THREADS of one process: the symmetric-memory
+    allocator hands every rank the same list of per-rank tensors (so a store into rank r's slab is a plain tensor
+    write), the cross-GPU barrier is a threading.Barrier, and the final row gather goes through a shared list."""
+
+    def __new__(cls, rank, world, shared, barrier):
+        from videocof_b200 import dist as vdist, ops
+
+        class SP(vdist.SequenceParallel):
+            def __init__(self):                      # no process group: set what __init__ would have set
+                self.group, self.world, self.rank = None, world, rank
+                self.kv_len = self.rows = None
+                self._kg = self._vg = None
+                self._pending, self._xbuf = {}, {}
+                self.attn_fn, self.copy_fn = ops.attention, ops.copy_blocked
+                self._push = self._push_key = None
+                self.alloc_fn = self._alloc
+
+            def _alloc(self, shape, like, group, tag):
+                with shared["lock"]:
+                    bufs = shared.setdefault(("buf", tag, tuple(shape)),
+                                             [torch.full(shape, float("nan"), dtype=like.dtype) for _ in range(world)])
+                return bufs[rank], bufs, barrier.wait
+
+            def all_gather_rows(self, y):
+                shared[("rows", rank)] = y.clone()
+                barrier.wait()
+                full = torch.cat([shared[("rows", r)] for r in range(world)], dim=0)
+                barrier.wait()
+                return full
+        return SP()
+
+
+@pytest.mark.parametrize("world,heads", [(2, 2), (4, 4)])
+def test_push_exchange_forward_matches_single_rank(world, heads, monkeypatch):
+    """VCOF_SP_MODE=push: Q, K, V land in the other ranks' receive buffers straight from the producing ops, the
+    attention output is pushed back by row chunk; the sharded forward equals the un-sharded one on every rank."""
+    import threading
+    vcof_emulator.install_dit(monkeypatch)
+    monkeypatch.setenv("VCOF_SP_MODE", "push")
+    ckw, shape, n_ctx, _ = DIT_CASES["dit_tiny"]
+    ckw = dict(ckw, num_heads=heads, dim=heads * (ckw["dim"] // ckw["num_heads"]))
+    cfg = DiTConfig(**ckw)
+    params = make_dit_params(cfg, seed=11)
+    shape = (shape[0], 3, 10, 6)                           # 45 tokens: padded to 46 / 48 rows
+    x, ctx, t = dit_inputs(shape, n_ctx, cfg.text_dim, 1, seed=23)
+    args = dict(x=x.bfloat16(), t=t, context=[c.bfloat16() for c in ctx], seq_len=45, **ROPE_MODES["cot"](3, 1))
+    with torch.no_grad():
+        single = build_model(cfg, params)(**args)
+    shared, barrier = {"lock": threading.Lock()}, threading.Barrier(world)
+    outs, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            model = build_model(cfg, params)
+            model._sp = _ThreadSP(rank, world, shared, barrier)
+            assert model._sp.use_push(heads)
+            with torch.no_grad():
+                outs[rank] = model(**args)
+                outs[rank] = model(**args)           # second forward: the receive buffers are reused
+        except Exception as e:                       # noqa: BLE001 - reported below, and the barrier is released
+            errs.append((rank, repr(e)))
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=300)
+    assert not errs, errs
+    for r in range(world):
+        assert outs[r] is not None and rel(outs[r], single) < 2e-3, (r, rel(outs[r], single))
+    # every receive buffer was completely overwritten by the pushes (they start as NaN)
+    for key, bufs in shared.items():
+        if isinstance(key, tuple) and key[0] == "buf":
+            assert all(not torch.isnan(b.float()).any() for b in bufs), key

@@ -297,6 +297,25 @@ def copy_blocked(rowmajor, blocked, to_blocked):
     return rowmajor
 
 
+def rmsnorm_rope_scatter(x, weight, eps, head_dim, rope, dests):
+    y = _rmsnorm_rope(x, weight, eps, head_dim, rope)
+    cp = x.shape[1] // len(dests)
+    for b, d in enumerate(dests):
+        d.copy_(y[:, b * cp:(b + 1) * cp])
+
+
+def copy_scatter(rowmajor, dests):
+    cp = rowmajor.shape[1] // len(dests)
+    for b, d in enumerate(dests):
+        d.copy_(rowmajor[:, b * cp:(b + 1) * cp])
+
+
+def copy_rows_scatter(src, dests):
+    rows = src.shape[0] // len(dests)
+    for c, d in enumerate(dests):
+        d.copy_(src[c * rows:(c + 1) * rows])
+
+
 def patchify(x):
     Cin, F, H, W = x.shape
     return x.view(Cin, F, H // 2, 2, W // 2, 2).permute(1, 2, 4, 0, 3, 5).reshape(F * (H // 2) * (W // 2), Cin * 4)
@@ -319,11 +338,14 @@ def linear_f32(x, w, bias=None, act_in=False, act_out=False):
     return torch.nn.functional.silu(v) if act_out else v
 
 
+DIT_OPS = ("gemm", "attention", "ln_modulate", "rmsnorm_rope_", "copy_blocked", "patchify", "unpatchify", "linear_f32",
+           "rmsnorm_rope_scatter", "copy_scatter", "copy_rows_scatter")
+
+
 def install_dit(monkeypatch):
     """Replace the libvcof entry points the DiT uses (videocof_b200/dit.py, dist.py) by the statements above."""
     from videocof_b200 import dit, ops
-    for name in ("gemm", "attention", "ln_modulate", "rmsnorm_rope_", "copy_blocked", "patchify", "unpatchify",
-                 "linear_f32"):
+    for name in DIT_OPS:
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(dit.WanTransformer3DModel, "_check_ready", lambda self, x: None)
 

@@ -37,4 +37,7 @@ done
 
 # 4. text encoder end to end
 run tests/native/selftest_t5 --bench "$OUT"
+# 5. (needs `gpurun --gpus 2`, not part of this 1-GPU call) the push exchange of the sequence-parallel path:
+#    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sp_check.py push
+#    VCOF_SP_MODE=push python -m torch.distributed.run ... bench.py --gpus 2 --steps 2 --warmup 3 --no-pipeline --no-cpu-baseline
 echo done

@@ -38,9 +38,13 @@ def main():
         model.enable_multi_gpus_inference()
         worst = 0.0
         report = {}
-        for mode in ("heads", "gather"):
+        # `sp_check.py push` adds the push exchange (symmetric memory, written without hardware at the end of round 1)
+        modes = ("heads", "gather") + (("push",) if "push" in sys.argv[1:] else ())
+        for mode in modes:
             os.environ["VCOF_SP_MODE"] = mode
             out = model(x=x, t=t, context=ctx, **kw)
+            if mode == "push":
+                out = model(x=x, t=t, context=ctx, **kw)      # second pass: the receive buffers are reused
             torch.cuda.synchronize()
             rel = float((out.float() - ref.float()).norm() / ref.float().norm())
             res = torch.tensor([rel], device=dev)

@@ -40,6 +40,10 @@ SIGNATURES = {
     "vcof_t5_rmsnorm": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_ll, c_int, c_float, c_void_p],
     "vcof_t5_attn": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_void_p,
                      c_int, c_int, c_int, c_int, c_void_p],
+    "vcof_rmsnorm_rope_scatter": [c_void_p, c_ll, c_void_p, c_int, c_void_p, c_float, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "vcof_copy_scatter": [c_void_p, c_ll, c_void_p, c_int, c_ll, c_int, c_void_p],
+    "vcof_copy_rows_scatter": [c_void_p, c_ll, c_void_p, c_int, c_ll, c_int, c_void_p],
     "vcof_cl_to_u8": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p],
     "vcof_u8_to_cl": [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p],
     "vcof_debug_frame_u8_host": [c_void_p, c_void_p, c_ll],

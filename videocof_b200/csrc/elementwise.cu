@@ -93,11 +93,21 @@ ln_modulate_kernel(const float* __restrict__ x, long long ldx, const float* __re
 constexpr int kRmsThreads = 128;
 constexpr int kRmsMaxVec = 8;  // uint4 (8 bf16) per thread -> C <= 8192
 
+// Destinations of a scattered column-blocked output: block b (cols_per_block columns of every row) is the dense
+// [rows, cols_per_block] slab at p[b].  Under sequence parallelism the slabs are the receive buffers of the other
+// ranks, mapped through NVLink peer memory: the kernel's own stores are the all-to-all.
+constexpr int kMaxScatter = 16;
+struct ScatterPtrs {
+  bf16* p[kMaxScatter];
+};
+
+template <bool SCATTER>
 __global__ void __launch_bounds__(kRmsThreads)
 rmsnorm_rope_kernel(bf16* __restrict__ x, long long ldx, const bf16* __restrict__ weight, float eps,
                     int C, int head_dim, const float2* __restrict__ table,
                     const int* __restrict__ tpos, int F, int H, int W, int n_t, int n_h,
-                    int row_offset, bf16* __restrict__ y, int cols_per_block, long long block_stride) {
+                    int row_offset, bf16* __restrict__ y, int cols_per_block, long long block_stride,
+                    const __grid_constant__ ScatterPtrs dst) {
   __shared__ float scratch[kRmsThreads / 32];
   const long long row = blockIdx.x;
   uint4* xr = reinterpret_cast<uint4*>(x + row * ldx);
@@ -158,7 +168,11 @@ rmsnorm_rope_kernel(bf16* __restrict__ x, long long ldx, const bf16* __restrict_
         o[e] = pack_bf16x2(yr, yi);
       }
       const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
-      if (y == nullptr) {
+      if constexpr (SCATTER) {
+        const int c = idx * 8;
+        const int blk = c / cols_per_block;
+        *reinterpret_cast<uint4*>(dst.p[blk] + row * cols_per_block + (c - blk * cols_per_block)) = ov;
+      } else if (y == nullptr) {
         xr[idx] = ov;
       } else {
         // column-blocked output [C / cols_per_block][rows][cols_per_block]: the send layout of the head exchange
@@ -185,6 +199,40 @@ copy_blocked_kernel(bf16* __restrict__ rowmajor, long long ld, bf16* __restrict_
     uint4* a = reinterpret_cast<uint4*>(rowmajor + row * ld + c);
     uint4* b = reinterpret_cast<uint4*>(blocked + blk * block_stride + row * cols_per_block + (c - blk * cols_per_block));
     if (to_blocked) *b = *a; else *a = *b;
+  }
+}
+
+// Pack of a row-major [rows, C] matrix into per-block destination slabs (see ScatterPtrs): the V leg of the
+// push-style head exchange.
+__global__ void __launch_bounds__(256)
+copy_scatter_kernel(const bf16* __restrict__ rowmajor, long long ld, const __grid_constant__ ScatterPtrs dst, long long rows, int C,
+                    int cols_per_block) {
+  const int nvec = C >> 3;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / nvec;
+    const int c = int(i - row * nvec) * 8;
+    const int blk = c / cols_per_block;
+    *reinterpret_cast<uint4*>(dst.p[blk] + row * cols_per_block + (c - blk * cols_per_block)) =
+        *reinterpret_cast<const uint4*>(rowmajor + row * ld + c);
+  }
+}
+
+// Row chunks of a dense [n_chunks * rows, cols] matrix to per-chunk destination slabs [rows, cols]: the return leg
+// of the push-style head exchange (chunk r = the query rows that rank r owns).
+__global__ void __launch_bounds__(256)
+copy_rows_scatter_kernel(const bf16* __restrict__ src, long long ld, const __grid_constant__ ScatterPtrs dst, long long rows, int cols,
+                         int n_chunks) {
+  const int nvec = cols >> 3;
+  const long long total = rows * n_chunks * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long grow = i / nvec;                 // row of src
+    const int c = int(i - grow * nvec) * 8;
+    const int chunk = int(grow / rows);
+    const long long r = grow - (long long)chunk * rows;
+    *reinterpret_cast<uint4*>(dst.p[chunk] + r * cols + c) = *reinterpret_cast<const uint4*>(src + grow * ld + c);
   }
 }
 
@@ -293,10 +341,10 @@ static int rmsnorm_rope_launch(void* x, long long ldx, const void* weight, float
                head_dim);
   VCOF_REQUIRE(rope_table == nullptr || (tpos != nullptr && n_t + n_h <= head_dim / 2),
                "vcof_rmsnorm_rope: rope requested without positions");
-  rmsnorm_rope_kernel<<<L, kRmsThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  rmsnorm_rope_kernel<false><<<L, kRmsThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<bf16*>(x), ldx, reinterpret_cast<const bf16*>(weight), eps, C, head_dim,
       reinterpret_cast<const float2*>(rope_table), tpos, F, H, W, n_t, n_h, row_offset,
-      reinterpret_cast<bf16*>(y), cols_per_block, block_stride);
+      reinterpret_cast<bf16*>(y), cols_per_block, block_stride, ScatterPtrs{});
   VCOF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -315,6 +363,71 @@ extern "C" int vcof_rmsnorm_rope_blocked(const void* x, long long ldx, void* y, 
   VCOF_REQUIRE(y != nullptr, "vcof_rmsnorm_rope_blocked: no output");
   return rmsnorm_rope_launch(const_cast<void*>(x), ldx, weight, eps, L, C, head_dim, rope_table, tpos, F, H, W, n_t,
                              n_h, row_offset, y, cols_per_block, block_stride, stream);
+}
+
+static int fill_scatter(ScatterPtrs* dst, void* const* ptrs, int n, const char* who) {
+  VCOF_REQUIRE(ptrs != nullptr && n >= 1 && n <= kMaxScatter, "%s: need 1..%d destination pointers, got %d", who,
+               kMaxScatter, n);
+  for (int i = 0; i < n; ++i) {
+    VCOF_REQUIRE(ptrs[i] != nullptr && (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) == 0,
+                 "%s: destination %d is null or not 16-byte aligned", who, i);
+    dst->p[i] = reinterpret_cast<bf16*>(ptrs[i]);
+  }
+  for (int i = n; i < kMaxScatter; ++i) dst->p[i] = nullptr;
+  return 0;
+}
+
+extern "C" int vcof_rmsnorm_rope_scatter(const void* x, long long ldx, void* const* block_ptrs, int n_blocks,
+                                         const void* weight, float eps, int L, int C, int head_dim,
+                                         const float* rope_table, const int* tpos, int F, int H, int W, int n_t,
+                                         int n_h, int row_offset, void* stream) {
+  ScatterPtrs dst;
+  if (int rc = fill_scatter(&dst, block_ptrs, n_blocks, "vcof_rmsnorm_rope_scatter")) return rc;
+  VCOF_REQUIRE(L > 0 && C > 0 && C % n_blocks == 0 && (C / n_blocks) % 8 == 0,
+               "vcof_rmsnorm_rope_scatter: C=%d must split into %d blocks of a multiple of 8 columns", C, n_blocks);
+  VCOF_REQUIRE(C % 8 == 0 && C <= kRmsThreads * kRmsMaxVec * 8 && ldx % 8 == 0,
+               "vcof_rmsnorm_rope_scatter: C=%d / ldx must be multiples of 8, C <= %d", C, kRmsThreads * kRmsMaxVec * 8);
+  VCOF_REQUIRE(head_dim % 8 == 0 && C % head_dim == 0, "vcof_rmsnorm_rope_scatter: bad head_dim %d", head_dim);
+  VCOF_REQUIRE(rope_table == nullptr || (tpos != nullptr && n_t + n_h <= head_dim / 2),
+               "vcof_rmsnorm_rope_scatter: rope requested without positions");
+  rmsnorm_rope_kernel<true><<<L, kRmsThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      const_cast<bf16*>(reinterpret_cast<const bf16*>(x)), ldx, reinterpret_cast<const bf16*>(weight), eps, C,
+      head_dim, reinterpret_cast<const float2*>(rope_table), tpos, F, H, W, n_t, n_h, row_offset, nullptr,
+      C / n_blocks, 0, dst);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vcof_copy_scatter(const void* rowmajor, long long ld, void* const* block_ptrs, int n_blocks,
+                                 long long rows, int C, void* stream) {
+  ScatterPtrs dst;
+  if (int rc = fill_scatter(&dst, block_ptrs, n_blocks, "vcof_copy_scatter")) return rc;
+  VCOF_REQUIRE(rows > 0 && C > 0 && ld % 8 == 0 && ld >= C && C % n_blocks == 0 && (C / n_blocks) % 8 == 0,
+               "vcof_copy_scatter: bad shape rows=%lld C=%d ld=%lld blocks=%d", rows, C, ld, n_blocks);
+  const long long total = rows * (C >> 3);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  copy_scatter_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(rowmajor), ld, dst, rows, C, C / n_blocks);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vcof_copy_rows_scatter(const void* src, long long ld, void* const* chunk_ptrs, int n_chunks,
+                                      long long rows, int cols, void* stream) {
+  ScatterPtrs dst;
+  if (int rc = fill_scatter(&dst, chunk_ptrs, n_chunks, "vcof_copy_rows_scatter")) return rc;
+  VCOF_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && ld >= cols,
+               "vcof_copy_rows_scatter: bad shape rows=%lld cols=%d ld=%lld", rows, cols, ld);
+  const long long total = rows * n_chunks * (cols >> 3);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  copy_rows_scatter_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(src), ld, dst, rows, cols, n_chunks);
+  VCOF_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int vcof_copy_blocked(void* rowmajor, long long ld, void* blocked, long long block_stride, long long rows,

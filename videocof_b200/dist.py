@@ -16,6 +16,13 @@ The head output is gathered at the end so every rank runs the identical schedule
 reference's xfuser USP path (videox_fun/dist/wan_xfuser.py:68-111, wan_transformer3d.py:802-816, :949-953,
 :1085-1086), which cannot run VideoCoF's chain-of-frames kwargs.
 
+* push exchange (opt-in, VCOF_SP_MODE=push; written at the end of round 1, NOT yet run on hardware): the head
+  exchange without a collective call.  Every rank owns receive buffers in symmetric (NVLink peer-mapped) memory; the
+  kernels that PRODUCE the exchanged tensors store straight into the other ranks' buffers — the norm/RoPE kernel for Q
+  and K (vcof_rmsnorm_rope_scatter), a pack kernel for V, a row-chunk copy for the attention output on the way back —
+  so the transfer overlaps the producing kernel store by store and costs no NCCL launch or staging pass; two
+  cross-GPU barriers per layer (stream-ordered, symmetric-memory signal pads) order producers against consumers.
+
 `attn_fn` / `copy_fn` are injectable so the sharding / exchange logic can be exercised on CPU with gloo
 (tests/test_dist_gloo.py); the product default is the libvcof tcgen05 kernel.
 """
@@ -23,6 +30,39 @@ import os
 
 import torch
 import torch.distributed as dist
+
+
+def symm_alloc(shape, like, group, tag):
+    """Symmetric-memory allocation for the push exchange: -> (local tensor, [the same buffer on every rank as a
+    peer-mapped tensor], barrier()).  torch.distributed._symmetric_memory maps the peers' allocations over NVLink
+    (CUDA VMM + fabric / fd handles); `barrier` is a stream-ordered cross-GPU barrier on the buffer's signal pad."""
+    import torch.distributed._symmetric_memory as symm
+    t = symm.empty(shape, dtype=like.dtype, device=like.device)
+    h = symm.rendezvous(t, group)
+    peers = [h.get_buffer(r, tuple(shape), like.dtype) for r in range(h.world_size)]
+    return t, peers, h.barrier
+
+
+class PushBuffers:
+    """Receive side of the push exchange for one (rows, C) problem.
+
+    recv[w] [P*rows, C/P] (w in q, k, v): all tokens in global order, this rank's heads — rank s stores its rows
+    [s*rows, (s+1)*rows) there; back [P, rows, C/P]: this rank's tokens, block s = the heads rank s attended over.
+    dst[w][r] / dst_back[r]: this rank's slab inside rank r's buffers (a peer-mapped tensor)."""
+
+    def __init__(self, sp, rows, C, like, alloc):
+        P, cp = sp.world, C // sp.world
+        mine = slice(sp.rank * rows, (sp.rank + 1) * rows)
+        self.recv, self.dst = {}, {}
+        for w in ("q", "k", "v"):
+            local, peers, barrier = alloc((P * rows, cp), like, sp.group, w)
+            self.recv[w] = local
+            self.dst[w] = [peers[r][mine] for r in range(P)]
+        local, peers, _ = alloc((P * rows, cp), like, sp.group, "b")
+        self.back = local.view(P, rows, cp)
+        self.dst_back = [peers[r][mine] for r in range(P)]
+        self.barrier = barrier
+        self.o = torch.empty((P * rows, cp), dtype=like.dtype, device=like.device)
 
 
 class SequenceParallel:
@@ -45,6 +85,9 @@ class SequenceParallel:
             copy_fn = ops.copy_blocked
         self.attn_fn = attn_fn
         self.copy_fn = copy_fn        # (rowmajor [rows,C], blocked [P,rows,C/P], to_blocked) pack / unpack kernel
+        self.alloc_fn = symm_alloc    # injectable like attn_fn / copy_fn (CPU tests share plain tensors between threads)
+        self._push = None
+        self._push_key = None
 
     def configure(self, kv_len, rows):
         """kv_len: number of real (non-padding) tokens of the full sequence; rows: tokens per rank."""
@@ -133,6 +176,29 @@ class SequenceParallel:
         back = self._buf("b", (P, rows, cp), q)
         dist.all_to_all_single(back.view(-1), o.view(-1), group=self.group)      # chunk r of o = rank r's tokens
         self.copy_fn(out, back, False)
+        return out
+
+    # -- push exchange (producer kernels store into the peers' receive buffers) -----------------------
+    def use_push(self, heads):
+        """VCOF_SP_MODE=push and heads divisible by P (otherwise the K/V all-gather serves)."""
+        return os.environ.get("VCOF_SP_MODE", "auto") == "push" and heads % self.world == 0
+
+    def push_buffers(self, rows, C, like):
+        key = (rows, C, like.dtype, str(like.device))
+        if self._push_key != key:
+            self._push = PushBuffers(self, rows, C, like, self.alloc_fn)
+            self._push_key = key
+        return self._push
+
+    def attention_pushed(self, heads, out, scatter_rows_fn):
+        """After every rank has pushed its Q, K, V slabs: barrier, attention over the full sequence for this rank's
+        heads/P heads, the output pushed back to the ranks that own the rows, barrier, unpack into out [rows, C]."""
+        pb = self._push
+        pb.barrier()
+        self.attn_fn(pb.recv["q"], pb.recv["k"], pb.recv["v"], heads // self.world, kv_len=self.kv_len, out=pb.o)
+        scatter_rows_fn(pb.o, pb.dst_back)
+        pb.barrier()
+        self.copy_fn(out, pb.back, False)
         return out
 
     def all_gather_rows(self, y):

@@ -127,6 +127,17 @@ class WanAttentionBlock(nn.Module):
             ops.rmsnorm_rope_(ws.q, sa.norm_q.weight, sa.eps, hd, rope)
             ops.rmsnorm_rope_(ws.k, sa.norm_k.weight, sa.eps, hd, rope)
             ops.attention(ws.q, ws.k, ws.v, n, kv_len=kv_len, out=ws.a)
+        elif sp.use_push(n):
+            # push exchange (dist.py): the producing kernels store Q, K, V straight into the other ranks' receive
+            # buffers over NVLink peer memory; no collective call, two stream-ordered barriers per layer
+            pb = sp.push_buffers(x.shape[0], self.dim, ws.a)
+            ops.gemm(ws.a, sa.v.weight, sa.v.bias, "bias", out=ws.v)
+            ops.copy_scatter(ws.v, pb.dst["v"])
+            ops.gemm(ws.a, sa.q.weight, sa.q.bias, "bias", out=ws.q)
+            ops.rmsnorm_rope_scatter(ws.q, sa.norm_q.weight, sa.eps, hd, rope, pb.dst["q"])
+            ops.gemm(ws.a, sa.k.weight, sa.k.bias, "bias", out=ws.k)
+            ops.rmsnorm_rope_scatter(ws.k, sa.norm_k.weight, sa.eps, hd, rope, pb.dst["k"])
+            sp.attention_pushed(n, ws.a, ops.copy_rows_scatter)
         elif sp.can_exchange_heads(n):
             # head exchange (dist.py): every projection lands in its all-to-all send layout — V through a pack
             # kernel, Q and K straight from the norm/RoPE kernel — and its exchange overlaps the next projection

@@ -5,6 +5,7 @@ arguments, allocates the output with torch, and launches exactly one libvcof ker
 the current CUDA stream.  No function has a PyTorch/CPU fallback — a CPU tensor or a
 missing libvcof.so raises.
 """
+import ctypes as _ct
 import math
 
 import torch
@@ -234,6 +235,48 @@ def copy_blocked(rowmajor, blocked, to_blocked):
     return blocked if to_blocked else rowmajor
 
 
+def _slabs(dests, rows, cols, what):
+    """Device addresses of dense bf16 [rows, cols] destination slabs (peer-mapped tensors under sequence parallelism)."""
+    if not 1 <= len(dests) <= 16:
+        raise _lib.VcofError(f"{what}: 1..16 destinations, got {len(dests)}")
+    for d in dests:
+        _chk(d, torch.bfloat16, what, 2)
+        if tuple(d.shape) != (rows, cols) or not d.is_contiguous():
+            raise _lib.VcofError(f"{what}: destination {tuple(d.shape)} is not a dense [{rows}, {cols}] slab")
+    return (_ct.c_void_p * len(dests))(*[d.data_ptr() for d in dests])
+
+
+def rmsnorm_rope_scatter(x, weight, eps, head_dim, rope, dests):
+    """rmsnorm_rope_ with the result scattered: column block b of every row goes to dests[b] (dense [L, C/len(dests)]
+    slabs — the receive buffers of the other ranks over NVLink peer memory); x is not modified."""
+    _chk(x, torch.bfloat16, "rmsnorm_rope_scatter.x", 2)
+    _chk(weight, torch.bfloat16, "rmsnorm_rope_scatter.weight", 1)
+    L, C = x.shape
+    arr = _slabs(dests, L, C // len(dests), "rmsnorm_rope_scatter.dests")
+    r = rope
+    _call("vcof_rmsnorm_rope_scatter", x.data_ptr(), x.stride(0), arr, len(dests), weight.data_ptr(), float(eps), L, C,
+          head_dim, _p(None if r is None else r.table), _p(None if r is None else r.tpos),
+          *((1, 1, 1, 0, 0, 0) if r is None else (r.F, r.H, r.W, r.n_t, r.n_h, r.row_offset)), _stream())
+
+
+def copy_scatter(rowmajor, dests):
+    """Column block b of the row-major bf16 [rows, C] matrix -> dests[b] (dense [rows, C/len(dests)] slabs)."""
+    _chk(rowmajor, torch.bfloat16, "copy_scatter.rowmajor", 2)
+    rows, C = rowmajor.shape
+    arr = _slabs(dests, rows, C // len(dests), "copy_scatter.dests")
+    _call("vcof_copy_scatter", rowmajor.data_ptr(), rowmajor.stride(0), arr, len(dests), rows, C, _stream())
+
+
+def copy_rows_scatter(src, dests):
+    """Row chunk c of the bf16 [len(dests) * rows, cols] matrix -> dests[c] (dense [rows, cols] slabs)."""
+    _chk(src, torch.bfloat16, "copy_rows_scatter.src", 2)
+    total, cols = src.shape
+    if total % len(dests):
+        raise _lib.VcofError(f"copy_rows_scatter: {total} rows do not split into {len(dests)} chunks")
+    arr = _slabs(dests, total // len(dests), cols, "copy_rows_scatter.dests")
+    _call("vcof_copy_rows_scatter", src.data_ptr(), src.stride(0), arr, len(dests), total // len(dests), cols, _stream())
+
+
 def patchify(x):
     """x bf16 [Cin,F,H,W] -> [F*(H/2)*(W/2), Cin*4] (column order c, ph, pw)."""
     _chk(x, torch.bfloat16, "patchify.x", 4)
@@ -271,9 +314,6 @@ def linear_f32(x, w, bias=None, act_in=False, act_out=False):
 # ------------------------------------------------------------------------------------------------
 # VAE ops (channels-last bf16 activations [T, H, W, C])
 # ------------------------------------------------------------------------------------------------
-import ctypes as _ct
-
-
 def _arr(ctype, vals):
     return (ctype * len(vals))(*vals)
 
