@@ -113,9 +113,18 @@ int vcof_rmsnorm_rope_scatter(const void* x, long long ldx, void* const* block_p
 int vcof_copy_scatter(const void* rowmajor, long long ld, void* const* block_ptrs, int n_blocks, long long rows, int C,
                       void* stream);
 
-/* Row chunks of a bf16 [n_chunks*rows, cols] matrix (pitch ld) to the slabs chunk_ptrs[c] ([rows, cols]). */
+/* Row chunks of a bf16 [n_chunks*rows, cols] matrix (pitch ld) to the slabs chunk_ptrs[c] ([rows, cols]): the unfused
+ * form of the return leg (attention into a local buffer, then this copy), kept for A/B against vcof_attn_fwd_scatter. */
 int vcof_copy_rows_scatter(const void* src, long long ld, void* const* chunk_ptrs, int n_chunks, long long rows,
                            int cols, void* stream);
+
+/* vcof_attn_fwd (natural V layout) with the output rows scattered: chunk c = query rows [c*rows_per_chunk,
+ * (c+1)*rows_per_chunk) is stored to the dense [rows_per_chunk, ldo] slab out_chunks[c] (HOST array of n_chunks <= 16
+ * device pointers).  Return leg of the push exchange: chunk c is the rows rank c owns and out_chunks[c] its receive
+ * buffer, so the attention epilogue's own stores carry the output over NVLink — compute and transfer in one kernel. */
+int vcof_attn_fwd_scatter(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                          void* const* out_chunks, int n_chunks, int rows_per_chunk, long long ldo, int Lq, int Lk,
+                          int kv_len, int heads, int head_dim, float softmax_scale, void* stream);
 
 /* Patchify latents x_bf16[Cin, F, H, W] -> tokens a_bf16[F*(H/2)*(W/2), Cin*4], column order
  * (c, ph, pw) = the flattened Conv3d weight [C, Cin, 1, 2, 2].  wan_transformer3d.py:870, 879. */

@@ -115,6 +115,12 @@ def test_c_abi_rejects_bad_arguments_with_a_message():
          "destination pointers"),
         ("vcof_rmsnorm_rope_scatter", (p, 256, ptrs, 3, p, 1e-6, 4, 256, 128, None, None, 1, 1, 1, 0, 0, 0, None),
          "blocks"),
+        ("vcof_attn_fwd_scatter", (p, 128, p, 128, p, 128, None, 2, 64, 128, 128, 128, 128, 1, 128, 0.09, None),
+         "output chunks"),
+        ("vcof_attn_fwd_scatter", (p, 128, p, 128, p, 128, ptrs, 2, 32, 128, 128, 128, 128, 1, 128, 0.09, None),
+         "do not cover"),
+        ("vcof_attn_fwd_scatter", (p, 128, p, 128, p, 128, ptrs, 2, 64, 128, 128, 128, 128, 1, 64, 0.09, None),
+         "head_dim"),
         ("vcof_copy_scatter", (p, 60, ptrs, 2, 4, 64, None), "vcof_copy_scatter"),
         ("vcof_copy_scatter", (p, 64, odd, 2, 4, 64, None), "aligned"),
         ("vcof_copy_rows_scatter", (p, 64, ptrs, 2, 0, 64, None), "vcof_copy_rows_scatter"),
@@ -133,6 +139,7 @@ def test_c_abi_rejects_bad_arguments_with_a_message():
         rc = getattr(lib, name)(*args)
         msg = lib.vcof_last_error().decode()
         assert rc < 0, (name, args, rc)
-        assert needle in msg and name in msg, (name, needle, msg)
+        base = "vcof_attn_fwd" if name == "vcof_attn_fwd_scatter" else name      # shared implementation, shared prefix
+        assert needle in msg and base in msg, (name, needle, msg)
         with pytest.raises(_lib.VcofError, match=name):
             _lib.call(name, *args)

@@ -75,3 +75,23 @@ def test_scatter_rejects_bad_destinations():
         ops.copy_rows_scatter(x, [torch.zeros(5, 256, dtype=torch.bfloat16, device=dev)] * 3)
     with pytest.raises(VcofError):
         ops.copy_scatter(x, [])
+
+
+@pytest.mark.parametrize("Lq,Lk,kv,heads,P", [(512, 640, 600, 2, 2), (1024, 1024, 1024, 3, 4), (300, 333, 333, 1, 1),
+                                                (2400, 777, 777, 2, 8)])
+def test_attention_scatter_equals_attention(Lq, Lk, kv, heads, P):
+    """The scattered epilogue changes store addresses only: chunk c of the output must equal rows
+    [c * Lq/P, (c+1) * Lq/P) of the plain kernel's output, bit for bit."""
+    from videocof_b200 import ops
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(Lq + heads)
+    C = heads * 128
+    q = torch.randn(Lq, C, generator=g).bfloat16().to(dev)
+    k = torch.randn(Lk, C, generator=g).bfloat16().to(dev)
+    v = torch.randn(Lk, C, generator=g).bfloat16().to(dev)
+    ref = ops.attention(q, k, v, heads, kv_len=kv)
+    rows = Lq // P
+    slabs = [torch.full((rows, C), 5.0, dtype=torch.bfloat16, device=dev) for _ in range(P)]
+    ops.attention_scatter(q, k, v, heads, slabs, kv_len=kv)
+    for c in range(P):
+        assert torch.equal(slabs[c], ref[c * rows:(c + 1) * rows]), c

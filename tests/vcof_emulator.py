@@ -241,6 +241,11 @@ def attention(q, k, v, heads, kv_len=None, scale=None, out=None, v_transposed=Fa
     return o
 
 
+def attention_scatter(q, k, v, heads, dests, kv_len=None, scale=None):
+    o = attention(q, k, v, heads, kv_len=kv_len, scale=scale)
+    copy_rows_scatter(o, dests)
+
+
 def ln_modulate(x, ln_w=None, ln_b=None, shift=None, scale=None, eps=1e-6, out=None):
     y = torch.nn.functional.layer_norm(x.float(), (x.shape[1],), ln_w, ln_b, eps)
     if scale is not None:
@@ -339,7 +344,7 @@ def linear_f32(x, w, bias=None, act_in=False, act_out=False):
 
 
 DIT_OPS = ("gemm", "attention", "ln_modulate", "rmsnorm_rope_", "copy_blocked", "patchify", "unpatchify", "linear_f32",
-           "rmsnorm_rope_scatter", "copy_scatter", "copy_rows_scatter")
+           "rmsnorm_rope_scatter", "copy_scatter", "copy_rows_scatter", "attention_scatter")
 
 
 def install_dit(monkeypatch):

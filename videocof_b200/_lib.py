@@ -42,6 +42,8 @@ SIGNATURES = {
                      c_int, c_int, c_int, c_int, c_void_p],
     "vcof_rmsnorm_rope_scatter": [c_void_p, c_ll, c_void_p, c_int, c_void_p, c_float, c_int, c_int, c_int, c_void_p,
                                   c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "vcof_attn_fwd_scatter": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_ll, c_int, c_int,
+                              c_int, c_int, c_int, c_float, c_void_p],
     "vcof_copy_scatter": [c_void_p, c_ll, c_void_p, c_int, c_ll, c_int, c_void_p],
     "vcof_copy_rows_scatter": [c_void_p, c_ll, c_void_p, c_int, c_ll, c_int, c_void_p],
     "vcof_cl_to_u8": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p],

@@ -43,6 +43,16 @@ struct AttnArgs {
   float scale_log2;
   bf16* out;
   long long ldo;
+  int rows_per_chunk;   // OUT_SCATTER only
+};
+
+// OUT_SCATTER: the output rows are split into chunks of rows_per_chunk consecutive query rows and chunk c is stored to
+// the dense [rows_per_chunk, ldo] slab p[c] instead of `out`.  Under the push exchange of the sequence-parallel path
+// (videocof_b200/dist.py) chunk c is the rows rank c owns and p[c] is its receive buffer, mapped through NVLink peer
+// memory: the return leg of the head exchange becomes the epilogue's own stores, overlapping the attention's tail.
+constexpr int kMaxOutChunks = 16;
+struct AttnOutChunks {
+  bf16* p[kMaxOutChunks];
 };
 
 constexpr int kAttnSmem = 2 * kTile + 2 * kKVStages * kTile + 256 + 1024;
@@ -95,10 +105,10 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // tcgen05.wait::ld) under the first 32 of the 64 first-half exponential pairs, and their shift + maximum is folded
 // into the other 32.  The check that decides whether the tile must be redone still covers all 128 columns and still
 // precedes the first publication of P, so the arithmetic is that of SPEC == 1.
-template <bool V_TRANS, int EMU, bool SPLIT_S, int PSPLIT, int SPEC = 0>
+template <bool V_TRANS, int EMU, bool SPLIT_S, int PSPLIT, int SPEC = 0, bool OUT_SCATTER = false>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
+                const __grid_constant__ CUtensorMap tmV, AttnArgs p, const __grid_constant__ AttnOutChunks oc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -629,7 +639,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       const float inv = 1.0f / l;
       const int row = q0 + t * kQT + row_in_tile;
-      bf16* orow = p.out + (long long)row * p.ldo + head * kHD;
+      bf16* orow;
+      if constexpr (OUT_SCATTER) {
+        const int chunk = row < p.Lq ? row / p.rows_per_chunk : 0;      // rows >= Lq are never stored
+        orow = oc.p[chunk] + (long long)(row - chunk * p.rows_per_chunk) * p.ldo + head * kHD;
+      } else {
+        orow = p.out + (long long)row * p.ldo + head * kHD;
+      }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t o[32];
@@ -664,10 +680,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 using namespace vcof;
 
-extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long long ldk,
-                             const void* v, long long ldv, void* out, long long ldo, int Lq, int Lk,
-                             int kv_len, int heads, int head_dim, float softmax_scale,
-                             int v_transposed, void* stream) {
+static int attn_fwd_impl(const void* q, long long ldq, const void* k, long long ldk,
+                         const void* v, long long ldv, void* out, long long ldo, int Lq, int Lk,
+                         int kv_len, int heads, int head_dim, float softmax_scale,
+                         int v_transposed, void* stream, const AttnOutChunks* chunks, int rows_per_chunk) {
   VCOF_REQUIRE(head_dim == kHD, "vcof_attn_fwd: head_dim %d unsupported (only 128)", head_dim);
   VCOF_REQUIRE(Lq > 0 && Lk > 0 && heads > 0, "vcof_attn_fwd: empty problem");
   VCOF_REQUIRE(kv_len >= 1 && kv_len <= Lk, "vcof_attn_fwd: kv_len %d outside [1, %d]", kv_len, Lk);
@@ -695,6 +711,8 @@ extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long l
   a.scale_log2 = softmax_scale * 1.4426950408889634f;
   a.out = reinterpret_cast<bf16*>(out);
   a.ldo = ldo;
+  a.rows_per_chunk = rows_per_chunk;
+  const AttnOutChunks oc = chunks != nullptr ? *chunks : AttnOutChunks{};
   const int items = a.heads * a.num_q_blocks;
   const int grid = items < sm_count() ? items : sm_count();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -709,9 +727,16 @@ extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long l
   }
   auto launch = [&](auto kern) -> int {
     VCOF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    kern<<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, a);
+    kern<<<grid, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, a, oc);
     return 0;
   };
+  if (chunks != nullptr) {     // push exchange: default arithmetic, natural V layout, scattered output rows
+    VCOF_REQUIRE(!v_transposed, "vcof_attn_fwd_scatter: natural V layout only");
+    const int lrc = launch(attn_fwd_kernel<false, 0, false, 2, 0, true>);
+    if (lrc) return lrc;
+    VCOF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   // VCOF_ATTN_SPLIT_S=1 / VCOF_ATTN_PSPLIT=2|4: tuning knobs (measured defaults: profiles/README.md)
   static int split_s = -1, psplit = -1;
   if (split_s < 0) {
@@ -741,4 +766,31 @@ extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long l
   if (lrc) return lrc;
   VCOF_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int vcof_attn_fwd(const void* q, long long ldq, const void* k, long long ldk,
+                             const void* v, long long ldv, void* out, long long ldo, int Lq, int Lk,
+                             int kv_len, int heads, int head_dim, float softmax_scale,
+                             int v_transposed, void* stream) {
+  return attn_fwd_impl(q, ldq, k, ldk, v, ldv, out, ldo, Lq, Lk, kv_len, heads, head_dim, softmax_scale, v_transposed,
+                       stream, nullptr, 0);
+}
+
+extern "C" int vcof_attn_fwd_scatter(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                                     long long ldv, void* const* out_chunks, int n_chunks, int rows_per_chunk,
+                                     long long ldo, int Lq, int Lk, int kv_len, int heads, int head_dim,
+                                     float softmax_scale, void* stream) {
+  VCOF_REQUIRE(out_chunks != nullptr && n_chunks >= 1 && n_chunks <= kMaxOutChunks,
+               "vcof_attn_fwd_scatter: need 1..%d output chunks, got %d", kMaxOutChunks, n_chunks);
+  VCOF_REQUIRE(rows_per_chunk > 0 && (long long)n_chunks * rows_per_chunk >= Lq,
+               "vcof_attn_fwd_scatter: %d chunks of %d rows do not cover Lq=%d", n_chunks, rows_per_chunk, Lq);
+  AttnOutChunks oc;
+  for (int i = 0; i < kMaxOutChunks; ++i) oc.p[i] = nullptr;
+  for (int i = 0; i < n_chunks; ++i) {
+    VCOF_REQUIRE(out_chunks[i] != nullptr && (reinterpret_cast<uintptr_t>(out_chunks[i]) & 15) == 0,
+                 "vcof_attn_fwd_scatter: output chunk %d is null or not 16-byte aligned", i);
+    oc.p[i] = reinterpret_cast<bf16*>(out_chunks[i]);
+  }
+  return attn_fwd_impl(q, ldq, k, ldk, v, ldv, out_chunks[0], ldo, Lq, Lk, kv_len, heads, head_dim, softmax_scale, 0,
+                       stream, &oc, rows_per_chunk);
 }

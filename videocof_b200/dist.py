@@ -19,7 +19,8 @@ reference's xfuser USP path (videox_fun/dist/wan_xfuser.py:68-111, wan_transform
 * push exchange (opt-in, VCOF_SP_MODE=push; written at the end of round 1, NOT yet run on hardware): the head
   exchange without a collective call.  Every rank owns receive buffers in symmetric (NVLink peer-mapped) memory; the
   kernels that PRODUCE the exchanged tensors store straight into the other ranks' buffers — the norm/RoPE kernel for Q
-  and K (vcof_rmsnorm_rope_scatter), a pack kernel for V, a row-chunk copy for the attention output on the way back —
+  and K (vcof_rmsnorm_rope_scatter), a pack kernel for V, the attention kernel's own epilogue for the output on the way
+  back (vcof_attn_fwd_scatter) —
   so the transfer overlaps the producing kernel store by store and costs no NCCL launch or staging pass; two
   cross-GPU barriers per layer (stream-ordered, symmetric-memory signal pads) order producers against consumers.
 
@@ -62,7 +63,6 @@ class PushBuffers:
         self.back = local.view(P, rows, cp)
         self.dst_back = [peers[r][mine] for r in range(P)]
         self.barrier = barrier
-        self.o = torch.empty((P * rows, cp), dtype=like.dtype, device=like.device)
 
 
 class SequenceParallel:
@@ -190,13 +190,13 @@ class SequenceParallel:
             self._push_key = key
         return self._push
 
-    def attention_pushed(self, heads, out, scatter_rows_fn):
+    def attention_pushed(self, heads, out, attn_scatter_fn):
         """After every rank has pushed its Q, K, V slabs: barrier, attention over the full sequence for this rank's
-        heads/P heads, the output pushed back to the ranks that own the rows, barrier, unpack into out [rows, C]."""
+        heads/P heads with the epilogue storing each row chunk straight into the buffer of the rank that owns the rows
+        (ops.attention_scatter: compute and return transfer in one kernel), barrier, unpack into out [rows, C]."""
         pb = self._push
         pb.barrier()
-        self.attn_fn(pb.recv["q"], pb.recv["k"], pb.recv["v"], heads // self.world, kv_len=self.kv_len, out=pb.o)
-        scatter_rows_fn(pb.o, pb.dst_back)
+        attn_scatter_fn(pb.recv["q"], pb.recv["k"], pb.recv["v"], heads // self.world, pb.dst_back, kv_len=self.kv_len)
         pb.barrier()
         self.copy_fn(out, pb.back, False)
         return out

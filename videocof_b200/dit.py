@@ -137,7 +137,7 @@ class WanAttentionBlock(nn.Module):
             ops.rmsnorm_rope_scatter(ws.q, sa.norm_q.weight, sa.eps, hd, rope, pb.dst["q"])
             ops.gemm(ws.a, sa.k.weight, sa.k.bias, "bias", out=ws.k)
             ops.rmsnorm_rope_scatter(ws.k, sa.norm_k.weight, sa.eps, hd, rope, pb.dst["k"])
-            sp.attention_pushed(n, ws.a, ops.copy_rows_scatter)
+            sp.attention_pushed(n, ws.a, ops.attention_scatter)
         elif sp.can_exchange_heads(n):
             # head exchange (dist.py): every projection lands in its all-to-all send layout — V through a pack
             # kernel, Q and K straight from the norm/RoPE kernel — and its exchange overlaps the next projection

@@ -161,6 +161,26 @@ def attention(q, k, v, heads, kv_len=None, scale=None, out=None, v_transposed=Fa
     return out
 
 
+def attention_scatter(q, k, v, heads, dests, kv_len=None, scale=None):
+    """attention() with the output rows scattered: row chunk c (Lq / len(dests) consecutive query rows) goes to
+    dests[c], dense bf16 [Lq / len(dests), heads*128] slabs (the owning ranks' receive buffers over NVLink peer memory)."""
+    _chk(q, torch.bfloat16, "attention_scatter.q", 2)
+    _chk(k, torch.bfloat16, "attention_scatter.k", 2)
+    _chk(v, torch.bfloat16, "attention_scatter.v", 2)
+    Lq, C = q.shape
+    if Lq % len(dests):
+        raise _lib.VcofError(f"attention_scatter: {Lq} query rows do not split into {len(dests)} chunks")
+    rows = Lq // len(dests)
+    arr = _slabs(dests, rows, C, "attention_scatter.dests")
+    Lk = k.shape[0]
+    hd = C // heads
+    kv_len = Lk if kv_len is None else kv_len
+    scale = 1.0 / math.sqrt(hd) if scale is None else scale
+    _call("vcof_attn_fwd_scatter", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+          arr, len(dests), rows, C, Lq, Lk, kv_len, heads, hd, float(scale), _stream(),
+          key=f"attn Lq={Lq} Lk={kv_len} heads={heads}")
+
+
 def ln_modulate(x, ln_w=None, ln_b=None, shift=None, scale=None, eps=1e-6, out=None):
     """bf16((LayerNorm(x) * ln_w + ln_b) * (1 + scale) + shift); x fp32 [L,C], vectors fp32 [C]."""
     _chk(x, torch.float32, "ln_modulate.x", 2)
