@@ -1,0 +1,192 @@
+"""Dry run of `-m gpu` test files on a CPU-only box (test infrastructure only; never imported by the product).
+
+The GPU box is reached a few times per round, so a GPU test that fails on a typo — a wrong argument order in a
+ctypes call, a shape slip in the test itself — wastes a whole call.  `fake_gpu()` lets the *unchanged* test functions
+run here:
+
+  * tensors asked onto "cuda" stay on the CPU (a TorchFunctionMode rewrites the device argument; `.cuda()` is the
+    identity) and `videocof_b200.ops` accepts them;
+  * `videocof_b200._lib.call` first calls the REAL libvcof.so, whose argument validation (include/vcof.h) runs before
+    anything touches a device: a validation failure (-1) is raised exactly as on the GPU, a CUDA failure (-2, no
+    device here) hands the call to the executable statement of the entry point's contract below;
+  * the statements decode the raw C arguments (pointers, pitches, sizes) in the order include/vcof.h declares them —
+    written from the header, not from ops.py, so a marshalling slip on either side shows up as a wrong result —
+    and do the arithmetic with tests/vcof_emulator.py.
+
+What a dry run proves: the test's own logic, ops.py's marshalling, the library's argument checks.  What it cannot:
+the kernels.  tests/test_gpu_dryrun_cpu.py lists the test files that are dry-run.
+"""
+import ctypes
+import types
+
+import torch
+from torch.overrides import TorchFunctionMode
+
+import vcof_emulator as emu
+
+_ITEM = {torch.bfloat16: 2, torch.float32: 4, torch.int32: 4, torch.uint8: 1, torch.int64: 8}
+
+
+def _flat(ptr, n, dtype):
+    """n elements of `dtype` at the host address `ptr`, sharing memory with whoever owns it."""
+    if n == 0:
+        return torch.empty(0, dtype=dtype)
+    buf = (ctypes.c_char * (n * _ITEM[dtype])).from_address(ptr)
+    return torch.frombuffer(buf, dtype=dtype, count=n)
+
+
+def _mat(ptr, rows, cols, ld, dtype=torch.bfloat16):
+    """[rows, cols] matrix with row pitch ld (elements) at ptr."""
+    return _flat(ptr, (rows - 1) * ld + cols, dtype).as_strided((rows, cols), (ld, 1))
+
+
+def _ptr_array(arr, n):
+    """A `void* const*` argument as ctypes handed it over (an array instance or an address)."""
+    if isinstance(arr, ctypes.Array):
+        return [int(arr[i]) for i in range(n)]
+    return [int(v) for v in (ctypes.c_void_p * n).from_address(int(arr))]
+
+
+def _rope(table, tpos, F, H, W, n_t, n_h, row_offset, head_dim):
+    if not table:
+        return None
+    return types.SimpleNamespace(table=_flat(table, 1024 * (head_dim // 2) * 2, torch.float32).view(1024, head_dim // 2, 2),
+                                 tpos=_flat(tpos, F, torch.int32), F=F, H=H, W=W, n_t=n_t, n_h=n_h,
+                                 row_offset=row_offset)
+
+
+# ---- one statement per entry point; parameter names and order are those of include/vcof.h ---------------------------
+def vcof_attn_fwd(q, ldq, k, ldk, v, ldv, out, ldo, Lq, Lk, kv_len, heads, head_dim, softmax_scale, v_transposed, stream):
+    C = heads * head_dim
+    vt = _mat(v, C, Lk, ldv) if v_transposed else _mat(v, Lk, C, ldv)
+    emu.attention(_mat(q, Lq, C, ldq), _mat(k, Lk, C, ldk), vt, heads, kv_len=kv_len, scale=softmax_scale,
+                  out=_mat(out, Lq, C, ldo), v_transposed=bool(v_transposed))
+
+
+def vcof_attn_fwd_scatter(q, ldq, k, ldk, v, ldv, out_chunks, n_chunks, rows_per_chunk, ldo, Lq, Lk, kv_len, heads,
+                          head_dim, softmax_scale, stream):
+    C = heads * head_dim
+    o = emu.attention(_mat(q, Lq, C, ldq), _mat(k, Lk, C, ldk), _mat(v, Lk, C, ldv), heads, kv_len=kv_len,
+                      scale=softmax_scale)
+    for c, p in enumerate(_ptr_array(out_chunks, n_chunks)):
+        r0, r1 = c * rows_per_chunk, min(Lq, (c + 1) * rows_per_chunk)
+        if r1 > r0:
+            _mat(p, r1 - r0, C, ldo).copy_(o[r0:r1])
+
+
+def vcof_rmsnorm_rope(x, ldx, weight, eps, L, C, head_dim, rope_table, tpos, F, H, W, n_t, n_h, row_offset, stream):
+    xm = _mat(x, L, C, ldx)
+    xm.copy_(emu._rmsnorm_rope(xm, _flat(weight, C, torch.bfloat16), eps, head_dim,
+                               _rope(rope_table, tpos, F, H, W, n_t, n_h, row_offset, head_dim)))
+
+
+def vcof_rmsnorm_rope_blocked(x, ldx, y, cols_per_block, block_stride, weight, eps, L, C, head_dim, rope_table, tpos, F, H,
+                              W, n_t, n_h, row_offset, stream):
+    r = emu._rmsnorm_rope(_mat(x, L, C, ldx), _flat(weight, C, torch.bfloat16), eps, head_dim,
+                          _rope(rope_table, tpos, F, H, W, n_t, n_h, row_offset, head_dim))
+    for b in range(C // cols_per_block):
+        _mat(y + 2 * b * block_stride, L, cols_per_block, cols_per_block).copy_(
+            r[:, b * cols_per_block:(b + 1) * cols_per_block])
+
+
+def vcof_rmsnorm_rope_scatter(x, ldx, block_ptrs, n_blocks, weight, eps, L, C, head_dim, rope_table, tpos, F, H, W, n_t,
+                              n_h, row_offset, stream):
+    r = emu._rmsnorm_rope(_mat(x, L, C, ldx), _flat(weight, C, torch.bfloat16), eps, head_dim,
+                          _rope(rope_table, tpos, F, H, W, n_t, n_h, row_offset, head_dim))
+    cp = C // n_blocks
+    for b, p in enumerate(_ptr_array(block_ptrs, n_blocks)):
+        _mat(p, L, cp, cp).copy_(r[:, b * cp:(b + 1) * cp])
+
+
+def vcof_copy_blocked(rowmajor, ld, blocked, block_stride, rows, C, cols_per_block, to_blocked, stream):
+    rm = _mat(rowmajor, rows, C, ld)
+    for b in range(C // cols_per_block):
+        blk = _mat(blocked + 2 * b * block_stride, rows, cols_per_block, cols_per_block)
+        cols = rm[:, b * cols_per_block:(b + 1) * cols_per_block]
+        blk.copy_(cols) if to_blocked else cols.copy_(blk)
+
+
+def vcof_copy_scatter(rowmajor, ld, block_ptrs, n_blocks, rows, C, stream):
+    rm = _mat(rowmajor, rows, C, ld)
+    cp = C // n_blocks
+    for b, p in enumerate(_ptr_array(block_ptrs, n_blocks)):
+        _mat(p, rows, cp, cp).copy_(rm[:, b * cp:(b + 1) * cp])
+
+
+def vcof_copy_rows_scatter(src, ld, chunk_ptrs, n_chunks, rows, cols, stream):
+    s = _mat(src, n_chunks * rows, cols, ld)
+    for c, p in enumerate(_ptr_array(chunk_ptrs, n_chunks)):
+        _mat(p, rows, cols, cols).copy_(s[c * rows:(c + 1) * rows])
+
+
+def vcof_cl_to_u8(x, ldx, out, npos, C, stream):
+    res = emu.cl_to_u8(_mat(x, npos, C, ldx).view(1, 1, npos, C), C)          # the library's host evaluation
+    _flat(out, npos * C, torch.uint8).copy_(res.reshape(-1))
+
+
+def vcof_u8_to_cl(frames, y, npos, C, Cp, stream):
+    res = emu.u8_to_cl(_flat(frames, npos * C, torch.uint8).view(1, 1, npos, C), Cp)
+    _flat(y, npos * Cp, torch.bfloat16).copy_(res.reshape(-1))
+
+
+STATEMENTS = {f.__name__: f for f in (vcof_attn_fwd, vcof_attn_fwd_scatter, vcof_rmsnorm_rope, vcof_rmsnorm_rope_blocked,
+                                      vcof_rmsnorm_rope_scatter, vcof_copy_blocked, vcof_copy_scatter,
+                                      vcof_copy_rows_scatter, vcof_cl_to_u8, vcof_u8_to_cl)}
+
+
+def _is_cuda(d):
+    if isinstance(d, torch.device):
+        return d.type == "cuda"
+    return isinstance(d, str) and d.split(":")[0] == "cuda"
+
+
+class _CudaIsCpu(TorchFunctionMode):
+    def __torch_function__(self, func, types_, args=(), kwargs=None):
+        kwargs = dict(kwargs or {})
+        if getattr(func, "__name__", "") == "cuda" and args and isinstance(args[0], torch.Tensor):
+            return args[0]
+        if _is_cuda(kwargs.get("device")):
+            kwargs["device"] = "cpu"
+        args = tuple("cpu" if _is_cuda(a) else a for a in args)
+        return func(*args, **kwargs)
+
+
+# ops.py functions replaced wholesale by tests/vcof_emulator.py: entry points with descriptor-style arguments (the VAE
+# convolutions) or already validated on hardware, which have no pointer-level statement here
+OPS_LEVEL = ("gemm", "ln_modulate", "patchify", "unpatchify", "linear_f32", "conv_igemm", "conv_lines", "rms_silu_cl",
+             "nchw_to_cl", "cl_to_nchw", "softmax_rows", "embed_rows", "t5_rmsnorm", "t5_attention")
+
+
+def install(monkeypatch):
+    """From here on "cuda" means the CPU and libvcof calls go real-validation-then-statement (module docstring).  Meant
+    for a whole pytest process (`pytest --gpu-dryrun`, tests/conftest.py): module-scoped fixtures move models to
+    "cuda" too.  Returns the object whose __exit__ undoes the device redirection."""
+    from videocof_b200 import _lib, ops
+
+    real_call = _lib.call
+
+    def call(name, *args):
+        if name.endswith("_host"):          # host-side debug entries (vcof_debug_*_host) run for real
+            return real_call(name, *args)
+        lib = _lib.load()
+        rc = getattr(lib, name)(*args)
+        msg = lib.vcof_last_error().decode()
+        if rc == -1 and "entry point unavailable" not in msg:
+            raise _lib.VcofError(f"{name} failed ({rc}): {msg}")
+        assert rc != 0, f"{name} succeeded without a GPU?"
+        if name not in STATEMENTS:
+            raise NotImplementedError(f"no pointer-level statement for {name}")
+        STATEMENTS[name](*[0 if a is None else a for a in args])
+
+    monkeypatch.setattr(_lib, "call", call)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    for name in OPS_LEVEL:
+        monkeypatch.setattr(ops, name, getattr(emu, name))
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    real_gen = torch.Generator
+    monkeypatch.setattr(torch, "Generator", lambda device="cpu": real_gen("cpu"))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    mode = _CudaIsCpu()
+    mode.__enter__()
+    return mode

@@ -1,0 +1,35 @@
+"""`-m gpu` test files, dry-run on the CPU (`pytest --gpu-dryrun`, tests/abi_emulator.py): the unchanged test functions
+run with "cuda" redirected to the CPU, libvcof's real argument validation in front of every call and the contract
+statements of the C ABI behind it.  Catches what does not need a GPU to be wrong — a test's own shape or index slip,
+a marshalling slip in videocof_b200/ops.py, an argument the library rejects — before a GPU call is spent on it.
+It says nothing about the kernels: those are the `-m gpu` runs proper.
+
+Deselected: tests that need a real "this tensor lives on the CPU" answer (`cpu` in their name: under the dry run every
+tensor claims to be a CUDA tensor), and the tcgen05 descriptor probe (no contract to state)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+FILES = [
+    ("test_widen_video_io_gpu.py", "not cpu", 15),          # written after the round-1 GPU budget was spent
+    ("test_widen_w_push_exchange_gpu.py", "not cpu", 10),   # idem
+    ("test_dit_gpu.py", "not cpu", 10),
+    ("test_kernels_gpu.py", "not umma and not cpu", 60),
+]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="a GPU is present: run the tests for real")
+@pytest.mark.parametrize("name,expr,at_least", FILES)
+def test_gpu_file_dry_runs(name, expr, at_least):
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, name), "--gpu-dryrun", "-q", "-x", "-k", expr,
+                        "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=1500,
+                       cwd=os.path.dirname(HERE))
+    tail = r.stdout[-3000:] + r.stderr[-1000:]
+    assert r.returncode == 0, tail
+    passed = int(r.stdout.rsplit(" passed", 1)[0].rsplit(None, 1)[-1])
+    assert passed >= at_least, tail

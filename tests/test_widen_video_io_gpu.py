@@ -120,8 +120,6 @@ def test_ops_reject_bad_arguments():
     from videocof_b200 import ops
     from videocof_b200._lib import VcofError
     with pytest.raises(VcofError):
-        ops.u8_to_cl(torch.zeros(1, 2, 2, 3, dtype=torch.uint8), 32)        # CPU tensor
-    with pytest.raises(VcofError):
         ops.u8_to_cl(torch.zeros(1, 2, 2, 3, device="cuda"), 32)            # not bytes
     with pytest.raises(VcofError):
         ops.u8_to_cl(torch.zeros(1, 2, 2, 3, dtype=torch.uint8, device="cuda"), 2)
@@ -129,6 +127,15 @@ def test_ops_reject_bad_arguments():
         ops.cl_to_u8(torch.zeros(1, 2, 2, 8, device="cuda"), 3)             # fp32
     with pytest.raises(VcofError):
         ops.cl_to_u8(torch.zeros(1, 2, 4, 8, dtype=torch.bfloat16, device="cuda")[:, :, ::2], 3)
+
+
+def test_ops_reject_cpu_tensor():
+    from videocof_b200 import ops
+    from videocof_b200._lib import VcofError
+    with pytest.raises(VcofError):
+        ops.u8_to_cl(torch.zeros(1, 2, 2, 3, dtype=torch.uint8), 32)
+    with pytest.raises(VcofError):
+        ops.cl_to_u8(torch.zeros(1, 2, 2, 8, dtype=torch.bfloat16), 3)
 
 
 @pytest.fixture(scope="module")

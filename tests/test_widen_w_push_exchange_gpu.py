@@ -70,11 +70,17 @@ def test_scatter_rejects_bad_destinations():
     with pytest.raises(VcofError):
         ops.rmsnorm_rope_scatter(x, w, 1e-6, 128, None, [torch.zeros(16, 64, dtype=torch.bfloat16, device=dev)] * 2)
     with pytest.raises(VcofError):
-        ops.copy_scatter(x, [torch.zeros(16, 128, dtype=torch.bfloat16)] * 2)          # CPU slab
-    with pytest.raises(VcofError):
         ops.copy_rows_scatter(x, [torch.zeros(5, 256, dtype=torch.bfloat16, device=dev)] * 3)
     with pytest.raises(VcofError):
         ops.copy_scatter(x, [])
+
+
+def test_scatter_rejects_cpu_slab():
+    from videocof_b200 import ops
+    from videocof_b200._lib import VcofError
+    x = torch.zeros(16, 256, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(VcofError):
+        ops.copy_scatter(x, [torch.zeros(16, 128, dtype=torch.bfloat16)] * 2)
 
 
 @pytest.mark.parametrize("Lq,Lk,kv,heads,P", [(512, 640, 600, 2, 2), (1024, 1024, 1024, 3, 4), (300, 333, 333, 1, 1),

@@ -168,7 +168,7 @@ def attention_scatter(q, k, v, heads, dests, kv_len=None, scale=None):
     _chk(k, torch.bfloat16, "attention_scatter.k", 2)
     _chk(v, torch.bfloat16, "attention_scatter.v", 2)
     Lq, C = q.shape
-    if Lq % len(dests):
+    if Lq % _ndest(dests, "attention_scatter.dests"):
         raise _lib.VcofError(f"attention_scatter: {Lq} query rows do not split into {len(dests)} chunks")
     rows = Lq // len(dests)
     arr = _slabs(dests, rows, C, "attention_scatter.dests")
@@ -255,10 +255,16 @@ def copy_blocked(rowmajor, blocked, to_blocked):
     return blocked if to_blocked else rowmajor
 
 
-def _slabs(dests, rows, cols, what):
-    """Device addresses of dense bf16 [rows, cols] destination slabs (peer-mapped tensors under sequence parallelism)."""
+def _ndest(dests, what):
+    """Number of destination slabs, checked before anything is divided by it."""
     if not 1 <= len(dests) <= 16:
         raise _lib.VcofError(f"{what}: 1..16 destinations, got {len(dests)}")
+    return len(dests)
+
+
+def _slabs(dests, rows, cols, what):
+    """Device addresses of dense bf16 [rows, cols] destination slabs (peer-mapped tensors under sequence parallelism)."""
+    _ndest(dests, what)
     for d in dests:
         _chk(d, torch.bfloat16, what, 2)
         if tuple(d.shape) != (rows, cols) or not d.is_contiguous():
@@ -272,7 +278,7 @@ def rmsnorm_rope_scatter(x, weight, eps, head_dim, rope, dests):
     _chk(x, torch.bfloat16, "rmsnorm_rope_scatter.x", 2)
     _chk(weight, torch.bfloat16, "rmsnorm_rope_scatter.weight", 1)
     L, C = x.shape
-    arr = _slabs(dests, L, C // len(dests), "rmsnorm_rope_scatter.dests")
+    arr = _slabs(dests, L, C // _ndest(dests, "rmsnorm_rope_scatter.dests"), "rmsnorm_rope_scatter.dests")
     r = rope
     _call("vcof_rmsnorm_rope_scatter", x.data_ptr(), x.stride(0), arr, len(dests), weight.data_ptr(), float(eps), L, C,
           head_dim, _p(None if r is None else r.table), _p(None if r is None else r.tpos),
@@ -283,7 +289,7 @@ def copy_scatter(rowmajor, dests):
     """Column block b of the row-major bf16 [rows, C] matrix -> dests[b] (dense [rows, C/len(dests)] slabs)."""
     _chk(rowmajor, torch.bfloat16, "copy_scatter.rowmajor", 2)
     rows, C = rowmajor.shape
-    arr = _slabs(dests, rows, C // len(dests), "copy_scatter.dests")
+    arr = _slabs(dests, rows, C // _ndest(dests, "copy_scatter.dests"), "copy_scatter.dests")
     _call("vcof_copy_scatter", rowmajor.data_ptr(), rowmajor.stride(0), arr, len(dests), rows, C, _stream())
 
 
@@ -291,7 +297,7 @@ def copy_rows_scatter(src, dests):
     """Row chunk c of the bf16 [len(dests) * rows, cols] matrix -> dests[c] (dense [rows, cols] slabs)."""
     _chk(src, torch.bfloat16, "copy_rows_scatter.src", 2)
     total, cols = src.shape
-    if total % len(dests):
+    if total % _ndest(dests, "copy_rows_scatter.dests"):
         raise _lib.VcofError(f"copy_rows_scatter: {total} rows do not split into {len(dests)} chunks")
     arr = _slabs(dests, total // len(dests), cols, "copy_rows_scatter.dests")
     _call("vcof_copy_rows_scatter", src.data_ptr(), src.stride(0), arr, len(dests), total // len(dests), cols, _stream())
