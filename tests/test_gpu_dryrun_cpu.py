@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 FILES = [
     ("test_widen_video_io_gpu.py", "not cpu", 15),          # written after the round-1 GPU budget was spent
     ("test_widen_w_push_exchange_gpu.py", "not cpu", 10),   # idem
-    ("test_widen_x_full_size_gpu.py", "c1", 9),             # idem; the c2 half needs the GPU (75 600 tokens)
+    ("test_widen_x_full_size_gpu.py", "c1 or small", 12),   # idem; the c2 / 720p half needs the GPU
     ("test_dit_gpu.py", "not cpu", 10),
     ("test_kernels_gpu.py", "not umma and not cpu", 60),
 ]

@@ -108,3 +108,55 @@ def test_cross_attention_every_element(cfg):
         return
     res = gpu_probe.run_case(dict(kind="attn", Lq=L, Lk=512, kv=512, heads=c["heads"], vt=0))
     assert res["ok"], res
+
+
+# ---- VAE convolutions at 720p -------------------------------------------------------------------------------------
+# The three layer shapes that carry the decoder's time at full resolution (68 % of the decoder in the
+# 96- and 192-channel 3x3x3 convolutions), on 5 frames of the 81 f x 720p clip — every output element against
+# torch.nn.functional.conv3d in fp32 on the GPU, rounded where the C-ABI contract rounds (tests/vcof_emulator.py:
+# bf16(acc + bias), + residual in fp32, clamp, bf16).  "small" is the same code on a 24 x 40 frame (dry-run on the CPU).
+VAE_LAYERS = {
+    "96_96_res": dict(cin=96, cout=96, res=True, div=1),         # full-resolution ResidualBlock conv (line-resident kernel)
+    "192_192": dict(cin=192, cout=192, res=False, div=2),        # half-resolution stage (tap-streaming kernel)
+    "head_96_3": dict(cin=96, cout=3, res=False, div=1, clamp=1.0, n_store=3),   # decoder head, clamp fused
+}
+
+
+@pytest.mark.parametrize("size", ["small", "720p"])
+@pytest.mark.parametrize("layer", list(VAE_LAYERS))
+@torch.no_grad()
+def test_vae_conv_every_element(size, layer):
+    import torch.nn.functional as Fn
+    from videocof_b200 import vae
+    c = VAE_LAYERS[layer]
+    H, W = ((24, 40) if size == "small" else (720, 1280))
+    T, H, W = 5, H // c["div"], W // c["div"]
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    conv = vae.CausalConv3d(c["cin"], c["cout"], (3, 3, 3), padding=(1, 1, 1))
+    conv.weight.data = (conv.weight.data * 3).bfloat16().float()
+    conv.bias.data = conv.bias.data.bfloat16().float()
+    conv = conv.to(dev)
+    gd = torch.Generator(device="cuda").manual_seed(T * H)
+    x = torch.randn(T, H, W, c["cin"], device=dev, generator=gd).bfloat16()
+    ldc = (c["cout"] + 7) // 8 * 8
+    res = torch.randn(T, H, W, ldc, device=dev, generator=gd).bfloat16() if c["res"] else None
+    got = vae.conv_causal(x, conv, residual=res, clamp=c.get("clamp", 0.0), n_store=c.get("n_store"))
+    torch.cuda.synchronize()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        xin = Fn.pad(x.permute(3, 0, 1, 2)[None].float(), (1, 1, 1, 1, 2, 0))      # causal in time, 'same' in space
+        ref = Fn.conv3d(xin, conv.weight.float(), conv.bias.float())[0].permute(1, 2, 3, 0)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    ref = ref.bfloat16().float()
+    if res is not None:
+        ref = ref + res[..., :c["cout"]].float()
+    if c.get("clamp"):
+        ref = ref.clamp(-c["clamp"], c["clamp"])
+    ref = ref.bfloat16().float()
+    g = got[..., :c["cout"]].float()
+    assert tuple(g.shape) == tuple(ref.shape)
+    rel = float((g - ref).norm() / ref.norm())
+    assert rel < 4e-3, rel                                     # tests/test_vae_gpu.py's single-op tolerance
