@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of a kernel-tuning session: parity of the core kernels for every queued variant, then the A/B timings
-# that decide them.  Python-free, ~1 minute of box time:
-#     gpurun --timeout 150 -- 'bash tools/r2_first_call.sh'
+# that decide them.  Steps 1-4 are Python-free (~1 minute of box time); 6-7 import torch:
+#     gpurun --timeout 600 -- 'bash tools/r2_first_call.sh'
 # Results land in gpurun_out/r2_first_call.jsonl (one JSON object per line, knobs recorded in each line).
 set -u
 cd "$(dirname "$0")/.."
@@ -40,4 +40,11 @@ run tests/native/selftest_t5 --bench "$OUT"
 # 5. (needs `gpurun --gpus 2`, not part of this 1-GPU call) the push exchange of the sequence-parallel path:
 #    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sp_check.py push
 #    VCOF_SP_MODE=push python -m torch.distributed.run ... bench.py --gpus 2 --steps 2 --warmup 3 --no-pipeline --no-cpu-baseline
+# 6. library baseline on the same GPU (plain PyTorch ops + flash-attn 2, one c2 block; the only step that imports torch):
+#    what the reference's own CUDA path would make of this B200, next to bench.py's numbers for libvcof
+echo "### python tools/torch_block_bench.py" | tee -a "$OUT"
+timeout 600 python tools/torch_block_bench.py | tee -a "$OUT"
+# 7. the GPU tests written after the round-1 budget was spent (each dry-run on the CPU beforehand)
+timeout 900 python -m pytest tests/test_widen_video_io_gpu.py tests/test_widen_w_push_exchange_gpu.py \
+    tests/test_widen_x_full_size_gpu.py -q 2>&1 | tail -15 | tee -a "$OUT"
 echo done
