@@ -119,16 +119,39 @@ class WanPipeline:
                                                                 max_sequence_length, device, dtype)
         return prompt_embeds, negative_prompt_embeds
 
-    def check_inputs(self, prompt, height, width, negative_prompt, prompt_embeds=None, negative_prompt_embeds=None):
-        """:430-480."""
+    _callback_tensor_inputs = ["latents", "prompt_embeds", "negative_prompt_embeds"]      # (:119-123)
+
+    def check_inputs(self, prompt, height, width, negative_prompt, callback_on_step_end_tensor_inputs,
+                     prompt_embeds=None, negative_prompt_embeds=None):
+        """:449-498 — same positional order, same conditions, ValueError as there."""
         if height % 8 != 0 or width % 8 != 0:
             raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if callback_on_step_end_tensor_inputs is not None and not all(
+                k in self._callback_tensor_inputs for k in callback_on_step_end_tensor_inputs):
+            bad = [k for k in callback_on_step_end_tensor_inputs if k not in self._callback_tensor_inputs]
+            raise ValueError(f"`callback_on_step_end_tensor_inputs` has to be in {self._callback_tensor_inputs}, "
+                             f"but found {bad}")
         if prompt is not None and prompt_embeds is not None:
-            raise ValueError("Cannot forward both `prompt` and `prompt_embeds`.")
-        if prompt is None and prompt_embeds is None:
-            raise ValueError("Provide either `prompt` or `prompt_embeds`.")
-        if prompt is not None and not isinstance(prompt, (str, list)):
+            raise ValueError("Cannot forward both `prompt` and `prompt_embeds`. Please make sure to only forward one "
+                             "of the two.")
+        elif prompt is None and prompt_embeds is None:
+            raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both `prompt` and "
+                             "`prompt_embeds` undefined.")
+        elif prompt is not None and not isinstance(prompt, (str, list)):
             raise ValueError(f"`prompt` has to be of type `str` or `list` but is {type(prompt)}")
+        if prompt is not None and negative_prompt_embeds is not None:
+            raise ValueError("Cannot forward both `prompt` and `negative_prompt_embeds`. Please make sure to only "
+                             "forward one of the two.")
+        if negative_prompt is not None and negative_prompt_embeds is not None:
+            raise ValueError("Cannot forward both `negative_prompt` and `negative_prompt_embeds`. Please make sure to "
+                             "only forward one of the two.")
+        if hasattr(prompt_embeds, "shape") and hasattr(negative_prompt_embeds, "shape"):
+            # (:492-498) tensors only: the pipeline's own form is a list of per-sample [tokens, 4096] tensors, whose
+            # token counts may differ between the prompt and the negative prompt
+            if prompt_embeds.shape != negative_prompt_embeds.shape:
+                raise ValueError("`prompt_embeds` and `negative_prompt_embeds` must have the same shape when passed "
+                                 f"directly, but got: `prompt_embeds` {prompt_embeds.shape} != "
+                                 f"`negative_prompt_embeds` {negative_prompt_embeds.shape}.")
 
     # ---- latents (:343-419) ------------------------------------------------------------------------------------
     def _encode_source(self, video, dtype, device):
@@ -183,7 +206,8 @@ class WanPipeline:
                  attention_kwargs=None, callback_on_step_end_tensor_inputs=("latents",), max_sequence_length=512,
                  comfyui_progressbar=False, shift=5, repeat_rope=True, cot=False):
         num_videos_per_prompt = 1
-        self.check_inputs(prompt, height, width, negative_prompt, prompt_embeds, negative_prompt_embeds)
+        self.check_inputs(prompt, height, width, negative_prompt, callback_on_step_end_tensor_inputs, prompt_embeds,
+                          negative_prompt_embeds)
         self._guidance_scale = guidance_scale
         self._interrupt = False
         device = self._execution_device
