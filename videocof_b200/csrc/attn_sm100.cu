@@ -419,16 +419,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mb += d;
             const float2 nd2 = make_float2(-d, -d);
 #pragma unroll
-            for (int c = 0; c < 64; ++c) x[c] = __fadd2_rn(x[c], nd2);
+            for (int c = 32; c < 64; ++c) x[c] = __fadd2_rn(x[c], nd2);
+            // First half: S_t(j) is still in TMEM (P is stored only below), so its 64 columns are reloaded here and
+            // shifted against the advanced reference — keeping their shifted values live through the common path for
+            // the sake of this branch cost 10-14 spilled registers (profiles/r1_sass_summary.txt).
+            const float2 nmbr = make_float2(-mb, -mb);
             acc0 = make_float2(0.f, 0.f);
             acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              float2 pr;
-              pr.x = ex2(x[c].x);
-              pr.y = ex2(x[c].y);
-              if (c & 1) acc1 = __fadd2_rn(acc1, pr); else acc0 = __fadd2_rn(acc0, pr);
-              pk[c] = pack_bf16x2(pr.x, pr.y);
+            for (int h = 0; h < 2; ++h) {        // 32 columns at a time: this branch must not set the register budget
+              uint32_t r[32];
+              tmem_ld32(tS + 32 * h, r);
+              tmem_ld_wait();
+              if (ragged) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (32 * h + c >= rem) r[c] = 0xff800000u;  // -inf
+              }
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float2 xr =
+                    __ffma2_rn(make_float2(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1])), sc2, nmbr);
+                float2 pr;
+                pr.x = ex2(xr.x);
+                pr.y = ex2(xr.y);
+                if (c & 1) acc1 = __fadd2_rn(acc1, pr); else acc0 = __fadd2_rn(acc0, pr);
+                pk[16 * h + c] = pack_bf16x2(pr.x, pr.y);
+              }
             }
           }
           tmem_st32(tS, pk);
@@ -519,16 +536,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mb += d;
             const float2 nd2 = make_float2(-d, -d);
 #pragma unroll
-            for (int c = 0; c < 64; ++c) x[c] = __fadd2_rn(x[c], nd2);
+            for (int c = 32; c < 64; ++c) x[c] = __fadd2_rn(x[c], nd2);
+            // First half: S_t(j) is still in TMEM (P is stored only below), so its 64 columns are reloaded here and
+            // shifted against the advanced reference — keeping their shifted values live through the common path for
+            // the sake of this branch cost 10-14 spilled registers (profiles/r1_sass_summary.txt).
+            const float2 nmbr = make_float2(-mb, -mb);
             acc0 = make_float2(0.f, 0.f);
             acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              float2 pr;
-              pr.x = ex2(x[c].x);
-              pr.y = ex2(x[c].y);
-              if (c & 1) acc1 = __fadd2_rn(acc1, pr); else acc0 = __fadd2_rn(acc0, pr);
-              pk[c] = pack_bf16x2(pr.x, pr.y);
+            for (int h = 0; h < 2; ++h) {        // 32 columns at a time: this branch must not set the register budget
+              uint32_t r[32];
+              tmem_ld32(tS + 32 * h, r);
+              tmem_ld_wait();
+              if (j == n_kv - 1 && rem < kKT) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (32 * h + c >= rem) r[c] = 0xff800000u;  // -inf
+              }
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float2 xr =
+                    __ffma2_rn(make_float2(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1])), sc2, nmbr);
+                float2 pr;
+                pr.x = ex2(xr.x);
+                pr.y = ex2(xr.y);
+                if (c & 1) acc1 = __fadd2_rn(acc1, pr); else acc0 = __fadd2_rn(acc0, pr);
+                pk[16 * h + c] = pack_bf16x2(pr.x, pr.y);
+              }
             }
           }
           tmem_st32(tS, pk);
