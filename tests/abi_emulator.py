@@ -1,7 +1,7 @@
 """Dry run of `-m gpu` test files on a CPU-only box (test infrastructure only; never imported by the product).
 
 The GPU box is reached a few times per round, so a GPU test that fails on a typo — a wrong argument order in a
-ctypes call, a shape slip in the test itself — wastes a whole call.  `fake_gpu()` lets the *unchanged* test functions
+ctypes call, a shape slip in the test itself — wastes a whole call.  `pytest --gpu-dryrun` (tests/conftest.py -> install() below) lets the *unchanged* test functions
 run here:
 
   * tensors asked onto "cuda" stay on the CPU (a TorchFunctionMode rewrites the device argument; `.cuda()` is the
@@ -12,6 +12,9 @@ run here:
   * the statements decode the raw C arguments (pointers, pitches, sizes) in the order include/vcof.h declares them —
     written from the header, not from ops.py, so a marshalling slip on either side shows up as a wrong result —
     and do the arithmetic with tests/vcof_emulator.py.
+
+Every entry point of include/vcof.h has a statement here except the two VAE convolutions (tap tables and 5-D views:
+their contract is stated one level up, on ops.conv_igemm / ops.conv_lines, in tests/vcof_emulator.py).
 
 What a dry run proves: the test's own logic, ops.py's marshalling, the library's argument checks.  What it cannot:
 the kernels.  tests/test_gpu_dryrun_cpu.py lists the test files that are dry-run.
@@ -129,9 +132,81 @@ def vcof_u8_to_cl(frames, y, npos, C, Cp, stream):
     _flat(y, npos * Cp, torch.bfloat16).copy_(res.reshape(-1))
 
 
+def vcof_gemm_bf16(a, lda, w, ldw, bias, gate, out, ldo, M, N, K, epilogue, stream):
+    epi = {v: k for k, v in _EPI.items()}[epilogue & 0xff]            # 0x100 = VCOF_GEMM_TILE128: same result
+    f32_out = epi in ("bias_gate_res", "bias_f32", "raw_f32")
+    emu.gemm(_mat(a, M, K, lda), _mat(w, N, K, ldw), _flat(bias, N, torch.bfloat16) if bias else None, epi,
+             out=_mat(out, M, N, ldo, torch.float32 if f32_out else torch.bfloat16),
+             gate=_flat(gate, N, torch.float32) if gate else None)
+
+
+def vcof_ln_modulate(x, ldx, ln_w, ln_b, shift, scale, out, ldo, L, C, eps, stream):
+    vec = lambda p: _flat(p, C, torch.float32) if p else None
+    emu.ln_modulate(_mat(x, L, C, ldx, torch.float32), vec(ln_w), vec(ln_b), vec(shift), vec(scale), eps,
+                    out=_mat(out, L, C, ldo))
+
+
+def vcof_patchify(x, a, Cin, F, H, W, stream):
+    src = _flat(x, Cin * F * H * W, torch.bfloat16).view(Cin, F, H, W)
+    _flat(a, Cin * F * H * W, torch.bfloat16).view(-1, Cin * 4).copy_(emu.patchify(src))
+
+
+def vcof_unpatchify(y, ldy, out, Cout, F, H, W, stream):
+    L = F * (H // 2) * (W // 2)
+    emu.unpatchify(_mat(y, L, 4 * Cout, ldy), Cout, F, H, W,
+                   out=_flat(out, Cout * F * H * W, torch.bfloat16).view(Cout, F, H, W))
+
+
+def vcof_linear_f32(x, w, bias, out, B, N, K, act_in, act_out, stream):
+    res = emu.linear_f32(_mat(x, B, K, K, torch.float32), _mat(w, N, K, K), _flat(bias, N, torch.bfloat16) if bias else None,
+                         act_in=bool(act_in), act_out=bool(act_out))
+    _mat(out, B, N, N, torch.float32).copy_(res)
+
+
+def vcof_softmax_rows(s, lds, p, ldp, rows, n, scale, stream):
+    _mat(p, rows, n, ldp).copy_(emu.softmax_rows(_mat(s, rows, n, lds, torch.float32), scale))
+
+
+def vcof_rms_silu_cl(x, ldx, gamma, y, ldy, npos, C, silu, stream):
+    emu.rms_silu_cl(_mat(x, npos, C, ldx), _flat(gamma, C, torch.float32), bool(silu), out=_mat(y, npos, C, ldy))
+
+
+def vcof_nchw_to_cl(x, y, C, Cp, thw, div, add, stream):
+    src = _flat(x, C * thw, torch.bfloat16).view(C, 1, 1, thw)
+    vec = lambda p: _flat(p, C, torch.float32) if p else None
+    _flat(y, thw * Cp, torch.bfloat16).view(1, 1, thw, Cp).copy_(emu.nchw_to_cl(src, Cp, vec(div), vec(add)))
+
+
+def vcof_cl_to_nchw(x, ldx, y, C, thw, sub, mul, stream):
+    vec = lambda p: _flat(p, C, torch.float32) if p else None
+    res = emu.cl_to_nchw(_mat(x, thw, ldx, ldx).view(1, 1, thw, ldx), C, vec(sub), vec(mul))
+    _flat(y, C * thw, torch.bfloat16).view(C, 1, 1, thw).copy_(res)
+
+
+def vcof_embed_rows(ids, table, ldt, vocab, out, ldo, n, C, stream):
+    emu.embed_rows(_flat(ids, n, torch.int64), _mat(table, vocab, C, ldt), out=_mat(out, n, C, ldo))
+
+
+def vcof_t5_rmsnorm(x, ldx, weight, y, ldy, rows, C, eps, stream):
+    emu.t5_rmsnorm(_mat(x, rows, C, ldx), _flat(weight, C, torch.bfloat16), eps, out=_mat(y, rows, C, ldy))
+
+
+def vcof_t5_attn(q, ldq, k, ldk, v, ldv, out, ldo, bias_rel, bias_ld, key_mask, B, L, heads, head_dim, stream):
+    C = heads * head_dim
+    bias = _mat(bias_rel, heads, 2 * L - 1, bias_ld, torch.float32)
+    emu.t5_attention(_mat(q, B * L, C, ldq), _mat(k, B * L, C, ldk), _mat(v, B * L, C, ldv), bias, B, L, heads,
+                     key_mask=_flat(key_mask, B * L, torch.int32) if key_mask else None, out=_mat(out, B * L, C, ldo))
+
+
+_EPI = {"bias": 0, "bias_gelu": 1, "bias_gate_res": 2, "bias_f32": 3, "raw_f32": 4, "gate_accum": 5, "mul": 6, "add": 7}
+
+
 STATEMENTS = {f.__name__: f for f in (vcof_attn_fwd, vcof_attn_fwd_scatter, vcof_rmsnorm_rope, vcof_rmsnorm_rope_blocked,
                                       vcof_rmsnorm_rope_scatter, vcof_copy_blocked, vcof_copy_scatter,
-                                      vcof_copy_rows_scatter, vcof_cl_to_u8, vcof_u8_to_cl)}
+                                      vcof_copy_rows_scatter, vcof_cl_to_u8, vcof_u8_to_cl, vcof_gemm_bf16,
+                                      vcof_ln_modulate, vcof_patchify, vcof_unpatchify, vcof_linear_f32, vcof_softmax_rows,
+                                      vcof_rms_silu_cl, vcof_nchw_to_cl, vcof_cl_to_nchw, vcof_embed_rows, vcof_t5_rmsnorm,
+                                      vcof_t5_attn)}
 
 
 def _is_cuda(d):
@@ -151,10 +226,9 @@ class _CudaIsCpu(TorchFunctionMode):
         return func(*args, **kwargs)
 
 
-# ops.py functions replaced wholesale by tests/vcof_emulator.py: entry points with descriptor-style arguments (the VAE
-# convolutions) or already validated on hardware, which have no pointer-level statement here
-OPS_LEVEL = ("gemm", "ln_modulate", "patchify", "unpatchify", "linear_f32", "conv_igemm", "conv_lines", "rms_silu_cl",
-             "nchw_to_cl", "cl_to_nchw", "softmax_rows", "embed_rows", "t5_rmsnorm", "t5_attention")
+# ops.py functions replaced wholesale by tests/vcof_emulator.py: the two VAE convolution entry points, whose
+# descriptor-style arguments (tap tables, 5-D views) have no pointer-level statement here
+OPS_LEVEL = ("conv_igemm", "conv_lines")
 
 
 def install(monkeypatch):
@@ -187,6 +261,8 @@ def install(monkeypatch):
     monkeypatch.setattr(torch, "Generator", lambda device="cpu": real_gen("cpu"))
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda device=None: types.SimpleNamespace(
+        multi_processor_count=148, name="dry run (CPU)", total_memory=180 << 30, major=10, minor=0))
     mode = _CudaIsCpu()
     mode.__enter__()
     return mode

@@ -5,7 +5,8 @@ a marshalling slip in videocof_b200/ops.py, an argument the library rejects — 
 It says nothing about the kernels: those are the `-m gpu` runs proper.
 
 Deselected: tests that need a real "this tensor lives on the CPU" answer (`cpu` in their name: under the dry run every
-tensor claims to be a CUDA tensor), and the tcgen05 descriptor probe (no contract to state)."""
+tensor claims to be a CUDA tensor), the tcgen05 descriptor probe (no contract to state), the full-size halves (75 600
+tokens / 720p: GPU only).  tests/test_lora_gpu.py is not dry-run (merge_lora asks the device object for its type)."""
 import os
 import subprocess
 import sys
@@ -15,23 +16,39 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-FILES = [
-    ("test_widen_video_io_gpu.py", "not cpu and not full_size", 14),   # written after the round-1 GPU budget was spent
+FILES = {
+    # file: (-k expression, minimum number of tests that must have run)
+    "test_widen_video_io_gpu.py": ("not cpu and not full_size", 14),      # written after the round-1 GPU budget was spent
     # (its 81 f x 720p table test also dry-runs — 20 s and 10 GB of host memory: `pytest --gpu-dryrun -k full_size`)
-    ("test_widen_w_push_exchange_gpu.py", "not cpu", 10),   # idem
-    ("test_widen_x_full_size_gpu.py", "c1 or small", 12),   # idem; the c2 / 720p half needs the GPU
-    ("test_dit_gpu.py", "not cpu", 10),
-    ("test_kernels_gpu.py", "not umma and not cpu", 60),
-]
+    "test_widen_w_push_exchange_gpu.py": ("not cpu", 10),                 # idem
+    "test_widen_x_full_size_gpu.py": ("c1 or small", 12),                 # idem; the c2 / 720p half needs the GPU
+    "test_dit_gpu.py": ("not cpu", 10),
+    "test_kernels_gpu.py": ("not umma and not cpu", 60),
+    "test_vae_gpu.py": ("not cpu", 27),
+    "test_pipeline_gpu.py": ("not cpu", 1),
+    "test_widen_text_encoder_gpu.py": ("not cpu", 23),
+}
+
+
+@pytest.fixture(scope="module")
+def runs():
+    """All files at once, one pytest process each (the dry run patches torch process-wide)."""
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    procs = {name: subprocess.Popen([sys.executable, "-m", "pytest", os.path.join(HERE, name), "--gpu-dryrun", "-q", "-x",
+                                     "-k", expr, "-p", "no:cacheprovider"], stdout=subprocess.PIPE,
+                                    stderr=subprocess.STDOUT, text=True, cwd=os.path.dirname(HERE), env=env)
+             for name, (expr, _) in FILES.items()}
+    yield procs
+    for p in procs.values():
+        if p.poll() is None:
+            p.kill()
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="a GPU is present: run the tests for real")
-@pytest.mark.parametrize("name,expr,at_least", FILES)
-def test_gpu_file_dry_runs(name, expr, at_least):
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, name), "--gpu-dryrun", "-q", "-x", "-k", expr,
-                        "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=1500,
-                       cwd=os.path.dirname(HERE))
-    tail = r.stdout[-3000:] + r.stderr[-1000:]
-    assert r.returncode == 0, tail
-    passed = int(r.stdout.rsplit(" passed", 1)[0].rsplit(None, 1)[-1])
-    assert passed >= at_least, tail
+@pytest.mark.parametrize("name", list(FILES))
+def test_gpu_file_dry_runs(runs, name):
+    out, _ = runs[name].communicate(timeout=1500)
+    tail = out[-3000:]
+    assert runs[name].returncode == 0, tail
+    passed = int(out.rsplit(" passed", 1)[0].rsplit(None, 1)[-1])
+    assert passed >= FILES[name][1], tail
