@@ -52,3 +52,26 @@ def test_gpu_file_dry_runs(runs, name):
     assert runs[name].returncode == 0, tail
     passed = int(out.rsplit(" passed", 1)[0].rsplit(None, 1)[-1])
     assert passed >= FILES[name][1], tail
+
+
+def test_statements_follow_the_header():
+    """Each contract statement takes the parameters of its entry point, by name and in the header's order (so the
+    statements are written against include/vcof.h, not against ops.py), and matches the ctypes binding's arity."""
+    import inspect
+    import re
+
+    import abi_emulator
+    from videocof_b200 import _lib
+    text = open(os.path.join(os.path.dirname(HERE), "include", "vcof.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = {m.group(1): m.group(2) for m in re.finditer(r"\bint\s+(vcof_\w+)\s*\(([^)]*)\)\s*;", text)}
+    without = {"vcof_conv_igemm", "vcof_conv_lines", "vcof_abi_version"}
+    for name, params in decls.items():
+        if name in without or name.startswith("vcof_debug"):
+            continue
+        assert name in abi_emulator.STATEMENTS, f"no contract statement for {name}"
+        want = [re.sub(r"\[.*\]", "", p.strip()).split()[-1].lstrip("*") for p in params.split(",")]
+        got = list(inspect.signature(abi_emulator.STATEMENTS[name]).parameters)
+        assert got == want, (name, got, want)
+        assert len(_lib.SIGNATURES[name]) == len(want), name
+    assert set(abi_emulator.STATEMENTS) <= set(decls)
