@@ -112,3 +112,30 @@ def test_teacache_and_cfg_skip_switches():
     assert (a.cfg_skip_ratio, a.current_steps, a.num_inference_steps) == (None, 0, None)
     b.disable_cfg_skip()
     assert (b.cfg_skip_ratio, b.current_steps, b.num_inference_steps) == (None, 0, None)
+
+
+@pytest.mark.parametrize("fmt", ["pth", "safetensors"])
+def test_vae_from_pretrained_adds_the_model_prefix(tmp_path, fmt, capsys):
+    """reference wan_vae.py:684-705 as the CLI calls it (fast_infer.py:300-303): one state-dict file whose keys lack the
+    `model.` prefix, `additional_kwargs` = the whole vae_kwargs section of the yaml (config/wan2.1/wan_civitai.yaml)."""
+    from oracle.vae_oracle import VAEConfig, make_vae_params
+    from videocof_b200.vae import AutoencoderKLWan
+    params = make_vae_params(VAEConfig(), seed=2)
+    bare = {k[len("model."):]: v.contiguous() for k, v in params.items()}
+    assert len(bare) == 194                                              # SURVEY §8b: 194 tensors
+    path = str(tmp_path / ("Wan2.1_VAE." + fmt))
+    if fmt == "pth":
+        torch.save(bare, path)
+    else:
+        from safetensors.torch import save_file
+        save_file(bare, path)
+    kw = {"vae_subpath": "Wan2.1_VAE.pth", "temporal_compression_ratio": 4, "spatial_compression_ratio": 8}
+    vae = AutoencoderKLWan.from_pretrained(path, additional_kwargs=kw).to(torch.bfloat16)
+    out = capsys.readouterr().out
+    assert "missing keys: 0" in out and "unexpected keys: 0" in out
+    sd = vae.state_dict()
+    assert set(sd) == set(params)
+    for k, v in params.items():
+        assert sd[k].dtype == torch.bfloat16 and torch.equal(sd[k], v.to(torch.bfloat16)), k
+    assert (vae.latent_channels, vae.temporal_compression_ratio, vae.spatial_compression_ratio) == (16, 4, 8)
+    assert vae.config.latent_channels == 16 and vae.dtype == torch.bfloat16
