@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 OUT=gpurun_out/r2_first_call.jsonl
 : > "$OUT"
 export KBENCH_OUT="$OUT"
-run() { echo "### $*" | tee -a "$OUT"; timeout 60 "$@" | tee -a "$OUT"; }
+run() { echo "### $*" | tee -a "$OUT"; timeout 120 "$@" | tee -a "$OUT"; }
 
 # 1. parity gates (default build first: it must stay green)
 run tests/native/selftest_core
