@@ -13,8 +13,7 @@ run here:
     written from the header, not from ops.py, so a marshalling slip on either side shows up as a wrong result —
     and do the arithmetic with tests/vcof_emulator.py.
 
-Every entry point of include/vcof.h has a statement here except the two VAE convolutions (tap tables and 5-D views:
-their contract is stated one level up, on ops.conv_igemm / ops.conv_lines, in tests/vcof_emulator.py).
+Every entry point of include/vcof.h has a statement here (the debug probes excepted).
 
 What a dry run proves: the test's own logic, ops.py's marshalling, the library's argument checks.  What it cannot:
 the kernels.  tests/test_gpu_dryrun_cpu.py lists the test files that are dry-run.
@@ -198,6 +197,48 @@ def vcof_t5_attn(q, ldq, k, ldk, v, ldv, out, ldo, bias_rel, bias_ld, key_mask, 
                      key_mask=_flat(key_mask, B * L, torch.int32) if key_mask else None, out=_mat(out, B * L, C, ldo))
 
 
+def _ints(ptr, n, ctype):
+    if isinstance(ptr, ctypes.Array):
+        return [int(ptr[i]) for i in range(n)]
+    return [int(v) for v in (ctype * n).from_address(int(ptr))]
+
+
+def _conv_common(x, x_dims, x_strides, geom_out, ldc, bias, residual, out, act_out, act_gamma, n_total, n_store):
+    """Tensors of a convolution call: the input storage the 5-D view addresses, and the output-addressed buffers."""
+    dims, strides = _ints(x_dims, 5, ctypes.c_longlong), _ints(x_strides, 4, ctypes.c_longlong)
+    extent = dims[0] + sum((d - 1) * st for d, st in zip(dims[1:], strides))
+    xs = _flat(x, extent, torch.bfloat16)
+    Tt, Hs, Ws = geom_out
+    buf = lambda p: _flat(p, Tt * Hs * Ws * ldc, torch.bfloat16).view(Tt, Hs, Ws, ldc) if p else None
+    return (xs, dims, strides, _flat(bias, n_total, torch.float32) if bias else None, buf(residual), buf(out), buf(act_out),
+            _flat(act_gamma, n_store, torch.float32) if act_gamma else None)
+
+
+def vcof_conv_igemm(x, x_dims, x_strides, w, k_total, taps, ntaps, tgroup, cin, geom, bias, residual, out, ldc, clamp,
+                    act_out, act_gamma, stream):
+    g = _ints(geom, 17, ctypes.c_int)
+    T, H, W, t_stride, n_total, n_tile, ot_mul, ot_add, oh_mul, oh_add, ow_mul, ow_add, Hs, Ws, half, n_store, kc = g
+    Tt = (T - 1) * ot_mul + ot_add + 1 + (1 if half > 0 else 0)
+    xs, dims, strides, b, res, o, act, gamma = _conv_common(x, x_dims, x_strides, (Tt, Hs, Ws), ldc, bias, residual, out,
+                                                            act_out, act_gamma, n_total, n_store)
+    flat = _ints(taps, 5 * ntaps, ctypes.c_short)
+    tap_list = [tuple(flat[5 * i:5 * i + 5]) for i in range(ntaps)]
+    wt = _flat(w, (k_total // kc) * n_total * kc, torch.bfloat16).view(k_total // kc, n_total, kc)
+    emu.conv_igemm(xs, dims, strides, wt, tap_list, cin, g[:16], b, o, residual=res, clamp=clamp, act_out=act,
+                   act_gamma=gamma, tgroup=tgroup)
+
+
+def vcof_conv_lines(x, x_dims, x_strides, w, cin, kt, t0, geom, bias, residual, out, ldc, clamp, act_out, act_gamma,
+                    stream):
+    g = _ints(geom, 7, ctypes.c_int)
+    T, H, W, n_total, n_tile, rows, n_store = g
+    xs, dims, strides, b, res, o, act, gamma = _conv_common(x, x_dims, x_strides, (T, H, W), ldc, bias, residual, out,
+                                                            act_out, act_gamma, n_total, n_store)
+    slices = (cin // 32) * kt * 9
+    wt = _flat(w, slices * n_total * 32, torch.bfloat16).view(slices, n_total, 32)
+    emu.conv_lines(xs, dims, strides, wt, cin, kt, t0, g, b, o, residual=res, clamp=clamp, act_out=act, act_gamma=gamma)
+
+
 _EPI = {"bias": 0, "bias_gelu": 1, "bias_gate_res": 2, "bias_f32": 3, "raw_f32": 4, "gate_accum": 5, "mul": 6, "add": 7}
 
 
@@ -206,7 +247,7 @@ STATEMENTS = {f.__name__: f for f in (vcof_attn_fwd, vcof_attn_fwd_scatter, vcof
                                       vcof_copy_rows_scatter, vcof_cl_to_u8, vcof_u8_to_cl, vcof_gemm_bf16,
                                       vcof_ln_modulate, vcof_patchify, vcof_unpatchify, vcof_linear_f32, vcof_softmax_rows,
                                       vcof_rms_silu_cl, vcof_nchw_to_cl, vcof_cl_to_nchw, vcof_embed_rows, vcof_t5_rmsnorm,
-                                      vcof_t5_attn)}
+                                      vcof_t5_attn, vcof_conv_igemm, vcof_conv_lines)}
 
 
 def _is_cuda(d):
@@ -226,9 +267,8 @@ class _CudaIsCpu(TorchFunctionMode):
         return func(*args, **kwargs)
 
 
-# ops.py functions replaced wholesale by tests/vcof_emulator.py: the two VAE convolution entry points, whose
-# descriptor-style arguments (tap tables, 5-D views) have no pointer-level statement here
-OPS_LEVEL = ("conv_igemm", "conv_lines")
+# ops.py functions replaced wholesale by tests/vcof_emulator.py instead of going through their wrapper: none any more
+OPS_LEVEL = ()
 
 
 def install(monkeypatch):
