@@ -11,7 +11,7 @@ N=${N:-2}
 OUT=gpurun_out/r2_multi_gpu_n$N.log
 : > "$OUT"
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-step() { echo "### $*" | tee -a "$OUT"; timeout "${T:-300}" "$@" 2>&1 | tail -25 | tee -a "$OUT"; echo "rc=$?" | tee -a "$OUT"; }
+step() { echo "### $*" | tee -a "$OUT"; timeout "${T:-300}" "$@" 2>&1 | tail -25 | tee -a "$OUT"; echo "rc=${PIPESTATUS[0]}" | tee -a "$OUT"; }
 
 step $TR --master-port 29511 tools/sp_check.py                      # heads + gather: validated in round 1, must stay ok
 T=120 step $TR --master-port 29512 tools/sp_check.py push           # + push exchange (symmetric memory)
