@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — denoising-steps/s of the VideoCoF hot path (Wan-2.1 14B DiT, 81 f x 720p latents).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl vcof|reference] [--workload c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl vcof|reference] [--workload c2|c3|c1|c5]
 
 One "step" = the pipeline's per-timestep work (reference videox_fun/pipeline/pipeline_wan.py:694-740):
 DiT forward on the [src | ground | target] latents with chain-of-frames RoPE, zero the source-frame
@@ -35,7 +35,10 @@ WORKLOADS = {
     "c1": (dict(dim=1536, ffn_dim=8960, num_heads=12, num_layers=30), (16, 5, 32, 32), 2, 77),
     # BASELINE.json configs[4]: 321 frames (4x length extrapolation) x 720p, meant for 8 GPUs
     "c5": (dict(dim=5120, ffn_dim=13824, num_heads=40, num_layers=40), (16, 81, 90, 160), 40, 77),
+    # BASELINE.json configs[2]: the inference.py path — guidance 5.0 -> batch 2 per step, 50-step schedule
+    "c3": (dict(dim=5120, ffn_dim=13824, num_heads=40, num_layers=40), (16, 21, 90, 160), 10, 77),
 }
+EXTRA = {"c3": dict(guidance=5.0, sched_steps=50)}
 METRIC = "denoising_steps_per_sec"
 
 
@@ -51,6 +54,13 @@ def measured_peaks():
         d = json.load(open(p))
         return dict(tflops=d.get("bf16_tflops_sustained", 1400.0), hbm=d.get("hbm_gbs", 6650.0), src="measured")
     return dict(tflops=1400.0, hbm=6650.0, src="fallback")
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 class ClockSampler:
@@ -105,6 +115,9 @@ def cpu_reference_sample(cfg_kw, L, Ls=1024, Lq=256):
     import torch
     from oracle.dit_oracle import DiTConfig, attention_ref, block_forward, make_block_params, rope_table, \
         temporal_positions
+    # all the host cores this process may use, whatever OMP_NUM_THREADS says: torch.distributed.run exports
+    # OMP_NUM_THREADS=1 to its workers, which made the N > 1 reference arm ten times slower than the N = 1 one
+    torch.set_num_threads(host_cores())
     cfg = DiTConfig(**cfg_kw)
     torch.manual_seed(0)
     p = make_block_params(cfg, 0, seed=1)
@@ -177,12 +190,77 @@ def l2_note(cfg_kw, rows):
 
 def workload_config(name, n_gpus):
     cfg_kw, lat, fs, n_ctx = WORKLOADS[name]
+    ex = EXTRA.get(name, {})
     L = lat[1] * (lat[2] // 2) * (lat[3] // 2)
+    batch = 2 if ex.get("guidance", 1.0) > 1.0 else 1
     return {"workload": f"{name}: Wan-2.1 DiT dim={cfg_kw['dim']} ffn={cfg_kw['ffn_dim']} heads={cfg_kw['num_heads']} "
                         f"layers={cfg_kw['num_layers']}, latents {list(lat)} -> {L} tokens, chain-of-frames "
-                        f"{fs}|1|{lat[1] - fs - 1}, 4-step UniPC schedule (shift 3), batch 1",
+                        f"{fs}|1|{lat[1] - fs - 1}, {ex.get('sched_steps', 4)}-step UniPC schedule (shift 3), "
+                        + (f"guidance {ex['guidance']} -> batch 2 (uncond + cond) per step" if batch == 2 else "batch 1"),
             "tokens": L, "parallelism": f"sp{n_gpus}" if n_gpus > 1 else "single",
             "l2": l2_note(cfg_kw, L // n_gpus)}
+
+
+def sha256_of(t):
+    """Checksum of a tensor's bytes (bf16 viewed as int16): equal across N when the sharded forward reproduces the
+    single-GPU bits, so every scaling record carries its own parity signal."""
+    import hashlib
+    import torch
+    return hashlib.sha256(t.detach().contiguous().view(torch.int16).cpu().numpy().tobytes()).hexdigest()
+
+
+class StepRunner:
+    """The per-timestep work of pipeline_wan.py:694-740 on one workload: DiT forward (batch 2 with classifier-free
+    guidance), source-frame velocity zeroed, UniPC step.  Host copies of the synthetic inputs are pinned."""
+
+    def __init__(self, torch, model, name, dev):
+        from videocof_b200.scheduler import FlowUniPCMultistepScheduler
+        self.torch, self.model, self.dev = torch, model, dev
+        cfg_kw, lat, fs, n_ctx = WORKLOADS[name]
+        ex = EXTRA.get(name, {})
+        self.fs, self.lat = fs, lat
+        self.guidance = ex.get("guidance", 1.0)
+        self.n_sched = ex.get("sched_steps", 4)
+        self.L = lat[1] * (lat[2] // 2) * (lat[3] // 2)
+        self.sched = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, solver_order=2)
+        g = torch.Generator(device="cpu").manual_seed(1)
+        self.lat_host = torch.randn(1, *lat, generator=g).to(torch.bfloat16).pin_memory()
+        self.ctx_host = torch.randn(n_ctx, 4096, generator=g).to(torch.bfloat16).pin_memory()
+        self.neg_host = torch.randn(n_ctx // 2, 4096, generator=g).to(torch.bfloat16).pin_memory()
+        self.B = 2 if self.guidance > 1.0 else 1
+        self.kw = dict(seq_len=self.L, frame_split_indices=[fs] * self.B,
+                       ground_frame_indices=[(fs, fs + 1)] * self.B)
+        self.reset()
+
+    def contexts(self, non_blocking=False):
+        c = [self.ctx_host.to(self.dev, non_blocking=non_blocking)]
+        if self.B == 2:      # pipeline_wan.py:606: in_prompt_embeds = negative + positive
+            c = [self.neg_host.to(self.dev, non_blocking=non_blocking)] + c
+        return c
+
+    def reset(self):
+        self.i = 0
+        self.latents = self.lat_host.to(self.dev)
+        self.ctx_dev = self.contexts()
+        self.sched.set_timesteps(self.n_sched, device=self.dev, shift=3.0)
+
+    def one_step(self, latents, ctx):
+        torch = self.torch
+        if self.i % self.n_sched == 0:
+            self.sched.set_timesteps(self.n_sched, device=self.dev, shift=3.0)
+        t = self.sched.timesteps[self.i % self.n_sched]
+        x = torch.cat([latents] * 2) if self.B == 2 else latents                 # (:700)
+        with torch.no_grad():
+            v = self.model(x=x, t=t.expand(self.B), context=ctx, **self.kw)
+        if self.B == 2:                                                            # (:731-733)
+            vu, vt = v.chunk(2)
+            v = vu + self.guidance * (vt - vu)
+        v[:, :, :self.fs] = 0                                                      # (:736)
+        self.i += 1
+        return self.sched.step(v, t, latents, return_dict=False)[0]
+
+    def resident_step(self):
+        self.latents = self.one_step(self.latents, self.ctx_dev)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -193,7 +271,6 @@ def run_vcof(args):
     import torch.distributed as dist
     from videocof_b200 import ops
     from videocof_b200.dit import WanTransformer3DModel
-    from videocof_b200.scheduler import FlowUniPCMultistepScheduler
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -206,34 +283,12 @@ def run_vcof(args):
         dist.init_process_group("nccl", device_id=dev)
 
     cfg_kw, lat, fs, n_ctx = WORKLOADS[args.workload]
-    f = lat[1]
-    L = f * (lat[2] // 2) * (lat[3] // 2)
     model = WanTransformer3DModel.random_init(device=dev, seed=0, **cfg_kw)
     if world > 1:
         model.enable_multi_gpus_inference()
-    sched = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, solver_order=2)
-
-    g = torch.Generator(device="cpu").manual_seed(1)
-    lat_host = torch.randn(1, *lat, generator=g).to(torch.bfloat16).pin_memory()
-    ctx_host = torch.randn(n_ctx, 4096, generator=g).to(torch.bfloat16).pin_memory()
-    kw = dict(seq_len=L, frame_split_indices=[fs], ground_frame_indices=[(fs, fs + 1)])
-
-    def new_schedule():
-        sched.set_timesteps(4, device=dev, shift=3.0)
-
-    state = {"latents": lat_host.to(dev), "i": 0}
-    ctx_dev = [ctx_host.to(dev)]
-    new_schedule()
-
-    def one_step(latents, ctx, i):
-        """pipeline_wan.py:700-740 for guidance 1.0 (batch 1)."""
-        if i % 4 == 0:
-            new_schedule()
-        t = sched.timesteps[i % 4]
-        with torch.no_grad():
-            v = model(x=latents, t=t.expand(1), context=ctx, **kw)
-        v[:, :, :fs] = 0
-        return sched.step(v, t, latents, return_dict=False)[0]
+    run = StepRunner(torch, model, args.workload, dev)
+    L, sched = run.L, run.sched
+    lat_host, ctx_host = run.lat_host, run.ctx_host
 
     def barrier():
         if world > 1:
@@ -253,15 +308,9 @@ def run_vcof(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    def resident_step():
-        state["latents"] = one_step(state["latents"], ctx_dev, state["i"])
-        state["i"] += 1
-
     for _ in range(args.warmup):
-        resident_step()
-    state["i"] = 0
-    state["latents"] = lat_host.to(dev)
-    new_schedule()
+        run.resident_step()
+    run.reset()
 
     clocks = ClockSampler(local)
     if rank == 0:
@@ -270,31 +319,30 @@ def run_vcof(args):
     ops.enable_timing()
     if args.profile_range:
         torch.cuda.profiler.start()      # ncu --profile-from-start off captures only the timed steps
-    total_ms = timed(args.steps, resident_step)
+    total_ms = timed(args.steps, run.resident_step)
     if args.profile_range:
         torch.cuda.profiler.stop()
     timing = ops.collect_timing()
     launches = ops.launches()
     clk = clocks.stop() if rank == 0 else None
+    latents_sha = sha256_of(run.latents)        # after exactly `steps` steps from the seeded start: same at every N
 
     # ---- end to end through the public API with host buffers
     out_host = torch.empty_like(lat_host)
-    e2e_state = {"i": 0}
 
     def e2e_step():
         x = lat_host.to(dev, non_blocking=True)
-        c = [ctx_host.to(dev, non_blocking=True)]
-        y = one_step(x, c, e2e_state["i"])
-        e2e_state["i"] += 1
+        c = run.contexts(non_blocking=True)
+        y = run.one_step(x, c)
         out_host.copy_(y, non_blocking=True)
 
-    new_schedule()
+    run.reset()
     e2e_ms = timed(args.steps, e2e_step)
 
-    # ---- whole pipeline through WanPipeline.__call__ (VAE encode -> 4 steps -> VAE decode x2), host in/out
+    # ---- whole pipeline through WanPipeline.__call__ (VAE encode -> 4 steps -> VAE decode x2), host in/out: the
+    #      frames/s half of BASELINE.json's metric, at every N (DiT token-sharded, VAE frame-sharded with halos)
     pipe_stats = None
-    # (default at N = 1; at N > 1 only with --pipeline: the scaling runs measure the step metric)
-    if not args.no_pipeline and args.workload != "c5" and (world == 1 or args.pipeline):
+    if not args.no_pipeline and args.workload == "c2":
         from videocof_b200.pipeline import WanPipeline
         from videocof_b200.vae import AutoencoderKLWan
         torch.manual_seed(2)
@@ -304,17 +352,17 @@ def run_vcof(args):
             vae.enable_temporal_sharding()          # the DiT is already sequence-parallel (see above)
         src_frames = 4 * fs - 3                                   # fs latent frames of source video
         H, W = lat[2] * 8, lat[3] * 8
+        g = torch.Generator(device="cpu").manual_seed(3)
         if args.pipeline_bytes:     # byte frames in and out (videocof_b200/video_io.py)
             video_host = torch.randint(0, 256, (1, src_frames, H, W, 3), generator=g, dtype=torch.uint8).pin_memory()
         else:
             video_host = (torch.rand(1, 3, src_frames, H, W, generator=g) * 2 - 1).to(torch.bfloat16).pin_memory()
-        gen = torch.Generator(device="cpu").manual_seed(4)
         t_axis = 1 if args.pipeline_bytes else 2
 
         def run_pipe():
             return pipe(video=video_host, prompt_embeds=[ctx_host.to(dev)], height=H, width=W,
                         source_frames=src_frames, reasoning_frames=4, num_inference_steps=4, guidance_scale=1.0,
-                        shift=3, repeat_rope=True, cot=True, generator=gen,
+                        shift=3, repeat_rope=True, cot=True, generator=torch.Generator(device="cpu").manual_seed(4),
                         output_type="uint8" if args.pipeline_bytes else "numpy")
 
         run_pipe()                                                # warm-up (allocator, weight packs)
@@ -322,17 +370,42 @@ def run_vcof(args):
         t0 = time.perf_counter()
         out = run_pipe()
         barrier()
-        dt = time.perf_counter() - t0
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
         n_edit = int(out.edit_videos.shape[t_axis])
+        import hashlib
+        import numpy as np
+        frames = np.ascontiguousarray(np.asarray(out.edit_videos))
         pipe_stats = {"seconds": dt, "frames_per_sec": n_edit / dt, "edit_frames": n_edit,
                       "ground_frames": int(out.ground_videos.shape[t_axis]), "source_frames": src_frames,
+                      "edit_frames_sha256": hashlib.sha256(frames.tobytes()).hexdigest(),
                       "what": ("WanPipeline.__call__: VAE encode(source, host uint8 frames) + 4 DiT steps + VAE "
                                "decode(ground) + VAE decode(edit) -> uint8 frames on the host; random-init weights"
                                if args.pipeline_bytes else
                                "WanPipeline.__call__: VAE encode(source, host bf16) + 4 DiT steps + VAE decode(ground) + "
                                "VAE decode(edit) -> fp32 numpy frames on the host; random-init weights")
                               + ("; DiT token-sharded, VAE frame-sharded with halos" if world > 1 else "")}
-        del vae, pipe, out
+        del vae, pipe, out, frames
+        torch.cuda.empty_cache()
+
+    # ---- BASELINE.json configs[4] (321 frames x 720p, 8 GPUs): one timed step of the same model on the long clip
+    c5_stats = None
+    if args.workload == "c2" and (args.c5 or (world == 8 and not args.no_c5)):
+        run5 = StepRunner(torch, model, "c5", dev)
+        run5.resident_step()
+        run5.reset()
+        ms5 = timed(2, run5.resident_step)
+        c5_stats = {"ms_per_step": ms5 / 2, "steps_per_sec": 2e3 / ms5, "steps": 2, "warmup": 1,
+                    "latents_sha256": sha256_of(run5.latents), "config": workload_config("c5", world)}
+        del run5
+        torch.cuda.empty_cache()
+
+    # ---- the reference's own CUDA path on this GPU (tools/gpu_reference.py; N = 1 only)
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference and args.workload in ("c2", "c3"):
+        gpu_ref = gpu_reference_leg(torch, model, cfg_kw, lat, fs, timing, total_ms / args.steps / run.B)
 
     if rank != 0:
         if world > 1:
@@ -357,28 +430,75 @@ def run_vcof(args):
         roof.update(ncu_traffic(attn_key[0]))
     gpu_ms = sum(ms for _, ms in timing.values())
     breakdown = sorted(((k, n, ms) for k, (n, ms) in timing.items()), key=lambda r: -r[2])[:8]
-    fl = flops_per_forward(cfg_kw, L)
+    fl = flops_per_forward(cfg_kw, L) * run.B
     line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args.workload, world),
-            "clocks": clk, "gpu_launches": launches,
+            "clocks": clk, "gpu_launches": launches, "latents_sha256": latents_sha,
             "e2e": {"value": 1000.0 / (e2e_ms / args.steps), "unit": "steps/s",
-                    "h2d_bytes_per_step": lat_host.numel() * 2 + ctx_host.numel() * 2,
+                    "h2d_bytes_per_step": lat_host.numel() * 2 + sum(c.numel() * 2 for c in run.ctx_dev),
                     "d2h_bytes_per_step": out_host.numel() * 2},
             "roofline": roof,
             "model_tflops": fl / (ms_per_step * 1e-3) / 1e12 / world,
             "model_frac_of_peak": fl / (ms_per_step * 1e-3) / 1e12 / world / peaks["tflops"],
             "pipeline": pipe_stats,
+            "frames_per_sec": pipe_stats["frames_per_sec"] if pipe_stats else None,
             "kernel_ms_per_step": gpu_ms / args.steps,
             "top_kernels": [{"key": k, "launches": n, "ms": round(ms, 3)} for k, n, ms in breakdown]}
+    if c5_stats:
+        line["c5"] = c5_stats
+    if gpu_ref:
+        line["gpu_reference"] = gpu_ref
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_sample(cfg_kw, L)
-        line["cpu_baseline"] = {"value": 1.0 / r["step_s"], "unit": "steps/s", "cores": r["cores"],
+        line["cpu_baseline"] = {"value": 1.0 / r["step_s"] / run.B, "unit": "steps/s", "cores": r["cores"],
                                 "kind": "port", "sample": r["sample"]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def gpu_reference_leg(torch, model, cfg_kw, lat, fs, timing, ours_forward_ms):
+    """`gpu_reference`: the UNMODIFIED reference modules (baseline/_ref) on this same GPU — one WanAttentionBlock of the
+    workload's widths at the workload's token count, its flash-attn 2 self-attention call and its cuBLAS Linears,
+    CUDA-event timed right after the libvcof arm — and libvcof's speed-up per op and per block."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import gpu_reference as gr
+    except Exception as exc:       # noqa: BLE001
+        return {"unavailable": f"tools/gpu_reference.py failed to import: {exc!r}"}
+    if not gr.available():
+        return {"unavailable": "baseline/_ref not staged (run __graft_entry__.build() where /root/reference is mounted)"}
+    torch.cuda.empty_cache()
+    clocks = ClockSampler(torch.cuda.current_device())
+    clocks.start()
+    try:
+        ref = gr.measure(cfg_kw, lat, fs, device=f"cuda:{torch.cuda.current_device()}")
+    except Exception as exc:       # noqa: BLE001
+        clocks.stop()
+        return {"unavailable": f"reference CUDA path failed: {exc!r}"}
+    ref["clocks"] = clocks.stop()
+    L = ref["tokens"]
+    layers = cfg_kw["num_layers"]
+
+    def ours(prefix):
+        hit = [(n, ms) for k, (n, ms) in timing.items() if k.startswith(prefix)]
+        return hit[0][1] / hit[0][0] if hit else None
+    o_attn = ours(f"attn Lq={L} Lk={L} ")
+    o_lin = ours(f"gemm[bias] M={L} N={cfg_kw['dim']} K={cfg_kw['dim']}")
+    o_f1 = ours(f"gemm[bias_gelu] M={L} N={cfg_kw['ffn_dim']}")
+    o_f2 = ours(f"gemm[bias_gate_res] M={L} N={cfg_kw['dim']} K={cfg_kw['ffn_dim']}")
+    ref["libvcof"] = {"block_ms": ours_forward_ms / layers,
+                      "block_note": "whole forward + scheduler step / layers (embeddings, head and scheduler included: "
+                                    "favours the reference)",
+                      "self_attention_ms": o_attn, "linear_cxc_ms": o_lin,
+                      "ffn_ms": (o_f1 + o_f2) if o_f1 and o_f2 else None}
+    ref["speedup"] = {"block": ref["block_ms"] / (ours_forward_ms / layers),
+                      "self_attention_vs_fa2": ref["self_attention_fa2_ms"] / o_attn if o_attn else None,
+                      "linear_cxc_vs_cublas": ref["linear_cxc_ms"] / o_lin if o_lin else None,
+                      "ffn_vs_cublas": ref["ffn_ms"] / (o_f1 + o_f2) if o_f1 and o_f2 else None}
+    return ref
 
 
 def ncu_traffic(attn_key):
@@ -408,8 +528,11 @@ def main():
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed steps (use with ncu --profile-from-start off)")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the WanPipeline (VAE + 4 steps) end-to-end leg")
-    ap.add_argument("--pipeline", action="store_true",
-                    help="also run the WanPipeline leg at N > 1 (DiT sequence-parallel, VAE frame-sharded)")
+    ap.add_argument("--pipeline", action="store_true", help="(kept for old command lines: the leg now runs at every N)")
+    ap.add_argument("--c5", action="store_true", help="also time one step of the 321-frame workload (default at N = 8)")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip the reference's own CUDA path (baseline/_ref: flash-attn 2 + cuBLAS) timed beside libvcof")
     ap.add_argument("--pipeline-bytes", action="store_true",
                     help="WanPipeline leg with uint8 frames in and out (conversions on the device) instead of bf16 in / "
                          "fp32 out")

@@ -90,3 +90,19 @@ def test_vae_decode_is_strictly_causal(vae_params):
     full = vae_decode(vae_params, cfg, z)
     part = vae_decode(vae_params, cfg, z[:, :2])
     assert torch.allclose(full[:, :5], part, atol=1e-5)
+
+
+def test_c1_full_first_forward(golden_dir):
+    """The oracle at FULL depth (1.3B widths, 30 layers, chain of frames) against the first DiT forward of the executed
+    reference pipeline run of tools/gen_golden_c1.py (tests/golden/c1_full.npz)."""
+    from gen_golden_c1 import DIT_SEED, c1_inputs
+    gold = np.load(os.path.join(golden_dir, "c1_full.npz"))
+    cfg = DiTConfig.wan_1_3b()
+    params = make_dit_params(cfg, seed=DIT_SEED)
+    _, embeds = c1_inputs()
+    x = torch.from_numpy(gold["init_latents"])
+    with torch.no_grad():
+        y = dit_forward(params, cfg, x, torch.tensor([999.0]), [embeds[0]], 1280, frame_split_indices=[2],
+                        ground_frame_indices=[(2, 3)])
+    want = torch.from_numpy(gold["velocity"][0])
+    assert float((y - want).norm() / want.norm()) < 1e-4

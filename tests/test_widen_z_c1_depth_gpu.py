@@ -1,0 +1,142 @@
+"""BASELINE.json configs[0] ("C1") at FULL depth on the GPU: the 1.3B DiT (30 layers) over the 4-step chain-of-frames
+schedule, bracketed by the VAE, against tests/golden/c1_full.npz — the outputs of the UNMODIFIED reference pipeline
+(pipeline_wan.py:518-799) run in fp32 on the CPU (tools/gen_golden_c1.py).
+
+What is asserted (floating point path, bf16 compute against an fp32 reference; tolerances stated here):
+  * the DiT's velocity at every step and the latents after every step: relative Frobenius error, printed per step so the
+    growth over 30 layers x 4 steps is on record (gpurun_out/c1_depth.jsonl); bound 4e-2 on the first forward (the
+    tolerance tests/test_dit_gpu.py uses for 2 layers vs fp32), 6e-2 on the final latents;
+  * decoded ground + edit frames: PSNR >= 40 dB (north_star's bar for the fast_infer.py 4-step path), both from the
+    shared initial latents and end to end from the source clip through libvcof's own VAE encoder;
+  * where baseline/_ref is staged: the reference's own CUDA path (bf16 autocast + flash-attn 2) on the same inputs —
+    libvcof must be as close to fp32 as that path is (err_ours <= 1.25 err_ref + 1e-3).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gpu_reference as gr
+from gen_golden_c1 import CALL, DIT_SEED, VAE_SEED, c1_inputs
+from oracle.dit_oracle import DiTConfig, make_dit_params
+from oracle.vae_oracle import VAEConfig, make_vae_params
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _log(**kw):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "c1_depth.jsonl"), "a") as fh:
+        fh.write(json.dumps(kw) + "\n")
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def psnr(a, b):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    return float(10 * torch.log10(1.0 / ((a - b) ** 2).mean().clamp_min(1e-20)))     # frames in [0, 1]
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return dict(np.load(os.path.join(golden_dir, "c1_full.npz")))
+
+
+@pytest.fixture(scope="module")
+def dit_params():
+    return make_dit_params(DiTConfig.wan_1_3b(), seed=DIT_SEED)
+
+
+@pytest.fixture(scope="module")
+def pipe(dit_params):
+    from videocof_b200.dit import WanTransformer3DModel
+    from videocof_b200.pipeline import WanPipeline
+    from videocof_b200.scheduler import FlowUniPCMultistepScheduler
+    from videocof_b200.vae import AutoencoderKLWan
+    dit = WanTransformer3DModel(**DiTConfig.wan_1_3b().to_kwargs())
+    dit.load_state_dict(dit_params, strict=True)
+    vae = AutoencoderKLWan()
+    vae.load_state_dict(make_vae_params(VAEConfig(), seed=VAE_SEED), strict=True)
+    dit, vae = dit.to("cuda", torch.bfloat16).eval(), vae.to("cuda", torch.bfloat16).eval()
+    return WanPipeline(None, None, vae, dit, FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1))
+
+
+def _run(pipe, init):
+    video, embeds = c1_inputs()
+    lat, vel = [], []
+    hook = pipe.transformer.register_forward_hook(lambda _m, _a, out: vel.append(out.detach().float().cpu().clone()))
+
+    def cb(_p, i, t, kw):
+        lat.append(kw["latents"].detach().float().cpu().clone())
+        return {}
+    try:
+        out = pipe(video=video.cuda().bfloat16(), prompt_embeds=[embeds[0].cuda().bfloat16()],
+                   latents=init.cuda().bfloat16(), callback_on_step_end=cb, **CALL)
+    finally:
+        hook.remove()
+    return torch.stack(lat), torch.stack(vel), out.videos.float()
+
+
+def test_c1_four_steps_30_layers_vs_reference_fp32(pipe, gold):
+    lat, vel, vid = _run(pipe, torch.from_numpy(gold["init_latents"]))
+    fs = 2
+    per_step = []
+    for i in range(4):
+        # the source frames' velocity is zeroed by the caller (:736); compare what the model produced everywhere
+        per_step.append(dict(step=i, velocity_rel=rel(vel[i], gold["velocity"][i]),
+                             latents_rel=rel(lat[i][:, :, fs:], gold["latents"][i][:, :, fs:])))
+    p = psnr(vid, gold["videos"].astype(np.float32))
+    _log(test="c1_four_steps", per_step=per_step, psnr_db=p)
+    assert tuple(vid.shape) == tuple(gold["videos"].shape) == (1, 3, 6, 256, 256)
+    assert per_step[0]["velocity_rel"] < 4e-2, per_step
+    assert all(s["velocity_rel"] < 6e-2 and s["latents_rel"] < 6e-2 for s in per_step), per_step
+    assert p >= 40.0, (p, per_step)
+
+
+def test_c1_end_to_end_from_the_source_clip(pipe, gold):
+    """libvcof's own VAE encoder in front: [encode(source clip) | the golden run's noise] -> 4 steps -> split decode."""
+    video, _ = c1_inputs()
+    with torch.no_grad():
+        src = pipe.vae.encode(video.cuda().bfloat16())[0].mode().float().cpu()
+    init = torch.from_numpy(gold["init_latents"]).clone()
+    e_src = rel(src, gold["src_latent"])
+    init[:, :, :2] = src
+    lat, _, vid = _run(pipe, init)
+    p = psnr(vid, gold["videos"].astype(np.float32))
+    _log(test="c1_end_to_end", src_latent_rel=e_src, final_latents_rel=rel(lat[3][:, :, 2:], gold["latents"][3][:, :, 2:]),
+         psnr_db=p)
+    assert e_src < 2e-2, e_src
+    assert p >= 40.0, p
+
+
+@pytest.mark.skipif(not gr.available(), reason="baseline/_ref not staged (tools/stage_reference.py)")
+def test_c1_model_30_layers_vs_reference_cuda_path(pipe, dit_params, gold):
+    """The first forward of the golden run (30 layers, [16,5,32,32], chain of frames, t = 999) three ways: the reference
+    in fp32 (the golden), the reference's own CUDA path (bf16 autocast, flash-attn 2, cuBLAS), libvcof."""
+    ns = gr.load()
+    cfg = DiTConfig.wan_1_3b()
+    _, embeds = c1_inputs()
+    x = torch.from_numpy(gold["init_latents"]).cuda().bfloat16()
+    ctx = [embeds[0].cuda().bfloat16()]
+    t = torch.tensor([999.0], device="cuda")
+    kw = dict(seq_len=1280, frame_split_indices=[2], ground_frame_indices=[(2, 3)])
+    ref = ns.dit.WanTransformer3DModel(**cfg.to_kwargs())
+    ref.load_state_dict(dit_params, strict=True)
+    ref = ref.to("cuda", torch.bfloat16).eval().requires_grad_(False)
+    ref.freqs = ref.freqs.to("cuda")
+    with torch.no_grad(), gr.autocast(), gr.backend("FLASH_ATTENTION"):
+        y_ref = ref(x=x, t=t, context=ctx, **kw).float()
+    del ref
+    with torch.no_grad():
+        y = pipe.transformer(x=x, t=t, context=ctx, **kw).float()
+    want = torch.from_numpy(gold["velocity"][0])
+    r = dict(err_ours=rel(y, want), err_ref=rel(y_ref, want), ours_vs_ref=rel(y, y_ref))
+    _log(test="c1_model_30_layers_three_way", **r)
+    assert r["err_ours"] <= 1.25 * r["err_ref"] + 1e-3, r
+    assert r["ours_vs_ref"] < 4e-2, r

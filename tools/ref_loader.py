@@ -5,8 +5,9 @@ are not installed and there is no network).  Its hot-path files 
 handful of diffusers names, so this module installs tiny in-memory stand-ins for those names
 and loads the files with importlib straight from the read-only mount.  Nothing is copied.
 
-Used only by tools/gen_golden.py in the build container; /root/reference does not exist on
-the GPU box, so nothing under tests/, bench.py or the product imports this at run time.
+Used by tools/gen_golden*.py in the build container and — against the staged, git-ignored copy
+baseline/_ref (tools/stage_reference.py) — by tools/gpu_reference.py on the GPU box, where it runs the
+reference's own CUDA path as the GPU performance / parity reference.  The product never imports it.
 """
 import importlib.util
 import os
@@ -16,7 +17,22 @@ import types
 import torch
 import torch.nn as nn
 
-REF = os.environ.get("VCOF_REFERENCE", "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference():
+    """$VCOF_REFERENCE, else the read-only mount of the build container, else the staged copy that travels to the
+    GPU box (baseline/_ref, git-ignored; tools/stage_reference.py)."""
+    env = os.environ.get("VCOF_REFERENCE")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_ROOT, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "videox_fun")):
+            return cand
+    return "/root/reference"
+
+
+REF = _find_reference()
 
 
 class _Config(dict):
@@ -127,33 +143,40 @@ def _load(modname, relpath):
 _cache = {}
 
 
-def load_reference():
-    """Returns a namespace with the reference's wan_transformer3d, wan_vae, fm_solvers_unipc modules."""
-    if _cache:
-        return _cache["ns"]
+def load_reference(pkg="videox_fun"):
+    """Returns a namespace with the reference's wan_transformer3d, wan_vae, fm_solvers_unipc modules.
+
+    `pkg` is the top-level name the files are registered under in sys.modules (their imports of each other are all
+    relative, so any name works): the golden generators keep "videox_fun"; tools/gpu_reference.py uses a private name
+    so that the repo's own `videox_fun` overlay stays importable in the same process."""
+    if pkg in _cache:
+        return _cache[pkg]
     if not os.path.isdir(REF):
         raise RuntimeError(f"{REF} not present: goldens can only be regenerated in the build container")
-    os.environ.setdefault("VIDEOX_ATTENTION_TYPE", "SDPA")  # flash-attn asserts CUDA (attention_utils.py:73)
+    if not torch.cuda.is_available():
+        os.environ.setdefault("VIDEOX_ATTENTION_TYPE", "SDPA")  # flash-attn asserts CUDA (attention_utils.py:73)
     install_shims()
-    pk = _mod("videox_fun")
+    pk = _mod(pkg)
     pk.__path__ = []
     for sub in ("models", "utils", "dist"):
-        m = _mod("videox_fun." + sub)
+        m = _mod(f"{pkg}.{sub}")
         m.__path__ = []
-    d = sys.modules["videox_fun.dist"]
+    d = sys.modules[f"{pkg}.dist"]
     for n in ("get_sequence_parallel_rank", "get_sequence_parallel_world_size", "get_sp_group",
               "usp_attn_forward", "xFuserLongContextAttention"):
         setattr(d, n, None)
-    cfgopt = _load("videox_fun.utils.cfg_optimization", "videox_fun/utils/cfg_optimization.py")
-    sys.modules["videox_fun.utils"].cfg_skip = cfgopt.cfg_skip
-    _load("videox_fun.models.attention_utils", "videox_fun/models/attention_utils.py")
-    _load("videox_fun.models.cache_utils", "videox_fun/models/cache_utils.py")
-    _mod("videox_fun.models.wan_camera_adapter", SimpleAdapter=None)
-    dit = _load("videox_fun.models.wan_transformer3d", "videox_fun/models/wan_transformer3d.py")
-    vae = _load("videox_fun.models.wan_vae", "videox_fun/models/wan_vae.py")
-    unipc = _load("videox_fun.utils.fm_solvers_unipc", "videox_fun/utils/fm_solvers_unipc.py")
-    ns = types.SimpleNamespace(dit=dit, vae=vae, unipc=unipc)
-    _cache["ns"] = ns
+    cfgopt = _load(f"{pkg}.utils.cfg_optimization", "videox_fun/utils/cfg_optimization.py")
+    sys.modules[f"{pkg}.utils"].cfg_skip = cfgopt.cfg_skip
+    attn = _load(f"{pkg}.models.attention_utils", "videox_fun/models/attention_utils.py")
+    _load(f"{pkg}.models.cache_utils", "videox_fun/models/cache_utils.py")
+    _mod(f"{pkg}.models.wan_camera_adapter", SimpleAdapter=None)
+    dit = _load(f"{pkg}.models.wan_transformer3d", "videox_fun/models/wan_transformer3d.py")
+    vae = _load(f"{pkg}.models.wan_vae", "videox_fun/models/wan_vae.py")
+    unipc = _load(f"{pkg}.utils.fm_solvers_unipc", "videox_fun/utils/fm_solvers_unipc.py")
+    ns = types.SimpleNamespace(dit=dit, vae=vae, unipc=unipc, attention_utils=attn, root=REF)
+    _cache[pkg] = ns
+    if pkg == "videox_fun":
+        _cache["ns"] = ns
     return ns
 
 
