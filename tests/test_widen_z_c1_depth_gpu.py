@@ -4,8 +4,8 @@ schedule, bracketed by the VAE, against tests/golden/c1_full.npz — the outputs
 
 What is asserted (floating point path, bf16 compute against an fp32 reference; tolerances stated here):
   * the DiT's velocity at every step and the latents after every step: relative Frobenius error, printed per step so the
-    growth over 30 layers x 4 steps is on record (gpurun_out/c1_depth.jsonl); bound 4e-2 on the first forward (the
-    tolerance tests/test_dit_gpu.py uses for 2 layers vs fp32), 6e-2 on the final latents;
+    growth over 30 layers x 4 steps is on record (gpurun_out/c1_depth.jsonl; measured on B200, profiles/
+    r2_gpurun2_c1_depth.jsonl: velocity 5.3e-3 ... 5.9e-3, latents 2.3e-3 ... 5.4e-3, PSNR 50.4 dB); bound 1.5e-2 on each;
   * decoded ground + edit frames: PSNR >= 40 dB (north_star's bar for the fast_infer.py 4-step path), both from the
     shared initial latents and end to end from the source clip through libvcof's own VAE encoder;
   * where baseline/_ref is staged: the reference's own CUDA path (bf16 autocast + flash-attn 2) on the same inputs —
@@ -94,8 +94,7 @@ def test_c1_four_steps_30_layers_vs_reference_fp32(pipe, gold):
     p = psnr(vid, gold["videos"].astype(np.float32))
     _log(test="c1_four_steps", per_step=per_step, psnr_db=p)
     assert tuple(vid.shape) == tuple(gold["videos"].shape) == (1, 3, 6, 256, 256)
-    assert per_step[0]["velocity_rel"] < 4e-2, per_step
-    assert all(s["velocity_rel"] < 6e-2 and s["latents_rel"] < 6e-2 for s in per_step), per_step
+    assert all(s["velocity_rel"] < 1.5e-2 and s["latents_rel"] < 1.5e-2 for s in per_step), per_step
     assert p >= 40.0, (p, per_step)
 
 

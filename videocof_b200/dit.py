@@ -239,22 +239,47 @@ def temporal_positions(f, frame_split=None, ground=None):
     return list(range(frame_split)) + list(range(f - frame_split))
 
 
-_rope_cache = {}
+_rope_cache = {}      # id(freqs) -> (freqs, _version, device, table); the entry HOLDS the tensor so its id stays unique
 
 
 def make_rope_spec(freqs, device, f, h, w, frame_split=None, ground=None, row_offset=0):
-    """Device tables for vcof_rmsnorm_rope from the model's complex128 `freqs` [1024, d/2]."""
-    key = (freqs.data_ptr(), freqs._version, str(device))
-    table = _rope_cache.get(key)
-    if table is None:
+    """Device tables for vcof_rmsnorm_rope from the model's complex128 `freqs` [1024, d/2].  The cos/sin table is
+    cached per `freqs` tensor object (enable_riflex / disable_riflex install a new tensor, an in-place edit bumps
+    `_version`); a few entries are kept so that several models do not evict each other."""
+    hit = _rope_cache.get(id(freqs))
+    if hit is not None and hit[0] is freqs and hit[1] == freqs._version and hit[2] == str(device):
+        table = hit[3]
+    else:
         fr = freqs.detach().to("cpu")
         table = torch.stack([fr.real, fr.imag], dim=-1).to(torch.float32).contiguous().to(device)
-        _rope_cache.clear()
-        _rope_cache[key] = table
+        if len(_rope_cache) >= 4:
+            _rope_cache.pop(next(iter(_rope_cache)))
+        _rope_cache[id(freqs)] = (freqs, freqs._version, str(device), table)
     c = freqs.shape[1]
     n_t, n_h = c - 2 * (c // 3), c // 3
     tpos = torch.tensor(temporal_positions(f, frame_split, ground), dtype=torch.int32, device=device)
     return ops.RopeSpec(table, tpos, f, h, w, n_t, n_h, row_offset)
+
+
+def _reference_init(name, shape, dim):
+    """Value the reference constructor + init_weights (:462, :1133-1155) leave in a parameter the checkpoint does not
+    hold (the reference loads with strict=False, so such parameters keep their initial values, :1282)."""
+    leaf = name.rsplit(".", 1)[-1]
+    if leaf == "modulation":
+        return torch.randn(shape) / dim ** 0.5
+    if leaf == "bias":
+        return torch.zeros(shape)
+    if len(shape) == 1:                                   # RMSNorm / LayerNorm gains
+        return torch.ones(shape)
+    w = torch.empty(shape)
+    if name == "head.head.weight":
+        return w.zero_()
+    if name.startswith(("text_embedding", "time_embedding")):
+        return nn.init.normal_(w, std=0.02)
+    if name == "patch_embedding.weight":
+        nn.init.xavier_uniform_(w.flatten(1))
+        return w
+    return nn.init.xavier_uniform_(w)
 
 
 class _Config(dict):
@@ -655,14 +680,32 @@ class WanTransformer3DModel(nn.Module):
             for fpath in files:
                 state.update(load_file(fpath))
         own = dict(model.named_parameters())
-        missing = []
+        # patch_embedding with a different number of input channels: overlapping channels copied, the rest zero (:1270-1273)
+        pe = state.get("patch_embedding.weight")
+        if pe is not None and tuple(pe.shape) != tuple(own["patch_embedding.weight"].shape) and pe.dim() == 5:
+            tgt = torch.zeros(tuple(own["patch_embedding.weight"].shape), dtype=pe.dtype)
+            n = min(tgt.shape[1], pe.shape[1])
+            if tuple(tgt[:, :n].shape) == tuple(pe[:, :n].shape):
+                tgt[:, :n] = pe[:, :n]
+                state["patch_embedding.weight"] = tgt
+        for key in list(state):
+            if key in own and tuple(state[key].shape) != tuple(own[key].shape):
+                print(key, "Size don't match, skip")                                       # (:1276-1280)
+                del state[key]
+        missing = [name for name in own if name not in state]
+        unexpected = sorted(set(state) - set(own))
+        if missing and low_cpu_mem_usage:
+            # the reference's meta-device loader refuses an incomplete checkpoint (:1222-1229)
+            raise ValueError(f"Cannot load {cls} from {pretrained_model_path} because the following keys are missing: \n "
+                             f"{', '.join(missing)}. \n Please make sure to pass `low_cpu_mem_usage=False` if you want "
+                             "to randomly initialize those weights or else make sure your checkpoint file is correct.")
         for name, prm in own.items():
             src = state.get(name)
-            if src is None or tuple(src.shape) != tuple(prm.shape):
-                missing.append(name)
-                src = torch.zeros(prm.shape)
+            if src is None:
+                src = _reference_init(name, tuple(prm.shape), model.dim)     # what init_weights left there (:1133-1155)
             mod, _, leaf = name.rpartition(".")
             target = model.get_submodule(mod) if mod else model
             setattr(target, leaf, nn.Parameter(src.to(torch_dtype), requires_grad=False))
-        print(f"### missing keys: {len(missing)}; \n### unexpected keys: {len(set(state) - set(own))};")
+        print(f"### missing keys: {len(missing)}; \n### unexpected keys: {len(unexpected)};")
+        print(missing)                                                                     # (:1283-1284)
         return model

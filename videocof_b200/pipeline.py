@@ -205,6 +205,9 @@ class WanPipeline:
                  negative_prompt_embeds=None, output_type="numpy", return_dict=False, callback_on_step_end=None,
                  attention_kwargs=None, callback_on_step_end_tensor_inputs=("latents",), max_sequence_length=512,
                  comfyui_progressbar=False, shift=5, repeat_rope=True, cot=False):
+        # a diffusers PipelineCallback / MultiPipelineCallbacks object names its own tensor inputs (:559-560)
+        if hasattr(callback_on_step_end, "tensor_inputs"):
+            callback_on_step_end_tensor_inputs = callback_on_step_end.tensor_inputs
         num_videos_per_prompt = 1
         self.check_inputs(prompt, height, width, negative_prompt, callback_on_step_end_tensor_inputs, prompt_embeds,
                           negative_prompt_embeds)
@@ -272,9 +275,15 @@ class WanPipeline:
                 kw = {"latents": latents, "prompt_embeds": prompt_embeds, "negative_prompt_embeds": negative_prompt_embeds}
                 outs = callback_on_step_end(self, i, t, {k: kw[k] for k in callback_on_step_end_tensor_inputs})
                 latents = outs.pop("latents", latents)
+                # (:747-748) popped like the reference does; like there, the DiT keeps the embeddings of step 0
+                prompt_embeds = outs.pop("prompt_embeds", prompt_embeds)
+                negative_prompt_embeds = outs.pop("negative_prompt_embeds", negative_prompt_embeds)
 
         ground_video = edit_video = None
-        out_video = latents
+        # any output_type other than "numpy" (or this repo's "uint8") decodes nothing: the reference then hands the INPUT
+        # clip back as `.videos` (:757-799, `video` is never reassigned); the final latents reach the caller through
+        # callback_on_step_end
+        out_video = video
         if output_type in ("numpy", "uint8"):
             # "uint8" (not in the reference): byte frames [B, T, H, W, 3] converted on the device; time is axis 1 there
             decode, t_axis = (self.decode_latents, 2) if output_type == "numpy" else (self.decode_frames, 1)
