@@ -242,20 +242,6 @@ int vcof_cl_to_u8(const void* x, long long ldx, unsigned char* out, long long np
 int vcof_u8_to_cl(const unsigned char* frames, void* y, long long npos, int C, int Cp, void* stream);
 
 /* ---- diagnostics ---------------------------------------------------------------------- */
-/* One 128x128x64 tcgen05 tile with hand-swizzled operands (no TMA): d_f32[128,128] =
- * a_bf16[128,64] x b_bf16[128,64]^T.  mode bit0: B staged MN-major; bit1: A fed from TMEM.
- * Pins the descriptor conventions the GEMM / attention kernels depend on. */
-int vcof_debug_umma_probe(const void* a, const void* b, float* d, int mode, void* stream);
-
-/* Sustained TMA box-load rate: in every CTA `producers` (1..4) lanes of different warps each stream `iters` boxes of
- * the given rank-2 / rank-5 bf16 view through their own shared-memory ring (~192 KB in flight in total, no compute);
- * cycles[cta] receives the elapsed SM clocks.  flags: bits 0-3 boxes per barrier round trip (0 = 1), bit 4 alternate two
- * copies of the tensor map, bit 5 poll with mbarrier.test_wait instead of try_wait.  Explains the feed-rate
- * ceilings quoted in profiles/ (rows of 64 B vs 128 B, strided pixel slices vs contiguous rows). */
-int vcof_debug_tma_probe(const void* base, int rank, const long long* dims, const long long* strides, const int* box,
-                         int swizzle_bytes, int iters, const int* coords, int step_dim, int step, int wrap,
-                         unsigned long long* cycles, int grid, int producers, int flags, void* stream);
-
 /* The per-element functions of vcof_cl_to_u8 / vcof_u8_to_cl evaluated on the HOST over host arrays (bf16 values as
  * raw 16-bit patterns): the CPU test suite pins the kernels' arithmetic exhaustively.  No product code calls these. */
 int vcof_debug_frame_u8_host(const unsigned short* host_bf16_bits, unsigned char* host_out, long long n);

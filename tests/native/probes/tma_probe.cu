@@ -3,8 +3,9 @@
 // per producer waits for them and frees the slots; nothing else runs.  Reports achieved bytes/clk/SM so a kernel's feed rate can be compared
 // with what the TMA unit can deliver for that box geometry (rows of 64 B vs 128 B, 2-D vs 5-D views).
 // Used by tools/tma_probe.py; results in profiles/.
-#include "vcof_common.cuh"
-#include "../../include/vcof.h"
+#include "../../../videocof_b200/csrc/vcof_common.cuh"
+#include "../../../include/vcof.h"
+#include "vcof_probes.h"
 
 namespace vcof {
 

@@ -11,8 +11,9 @@
 //             128-row window starting `shift` rows in (a row-shifted view of a resident tile, as an im2col-free
 //             convolution would take one per filter tap); bit 7: put (start_address >> 7) & 7 into the descriptor's
 //             base-offset field (bits 49-51)
-#include "vcof_common.cuh"
-#include "../../include/vcof.h"
+#include "../../../videocof_b200/csrc/vcof_common.cuh"
+#include "../../../include/vcof.h"
+#include "vcof_probes.h"
 
 namespace vcof {
 

@@ -8,7 +8,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from videocof_b200 import _lib  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from videocof_b200 import _lib as _product  # noqa: E402
+import probe_lib as _lib  # noqa: E402
 
 
 def run(name, base, dims, strides, box, swz, iters, coords, step_dim, step, wrap, grid=148, producers=1, flags=0):
@@ -23,7 +25,7 @@ def run(name, base, dims, strides, box, swz, iters, coords, step_dim, step, wrap
         torch.cuda.synchronize()
         _lib.call("vcof_debug_tma_probe", *args)
         torch.cuda.synchronize()
-    except _lib.VcofError as e:           # e.g. the ring does not fit this many producers
+    except _product.VcofError as e:           # e.g. the ring does not fit this many producers
         print(json.dumps(dict(case=name, producers=producers, skipped=str(e)[-60:])), flush=True)
         return
     nbytes = 2 * max(flags & 15, 1)

@@ -10,7 +10,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from videocof_b200 import _lib  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import probe_lib as _lib  # noqa: E402  (tests/native/libvcof_probes.so)
 
 
 def main():

@@ -92,8 +92,9 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 }
 
 // EMU: of every 8 element pairs, this many take the polynomial path (0 = all MUFU).
-// SPLIT_S: S_t = Q_t K_j^T is issued as two N=64 halves with separate barriers, so the softmax warps load and
-// reduce the first 64 score columns while the tensor pipe still computes the second half.
+// SPLIT_S: S_t(j+1) = Q_t K_{j+1}^T is issued as two N = 64 halves; the half that lands in score columns 64..127 —
+// which P_t(j) does not alias — is issued as soon as the softmax warps have S_t(j) in registers, i.e. under the
+// exponentials of step j, and only the other half follows PV_t(j) on the tile's dependency chain.
 // PSPLIT: number of K-chunks (2 or 4) in which P is published to the PV MMA.
 // SPEC (experimental, VCOF_ATTN_SPEC=1, not yet run on hardware): the row maximum leaves the critical path.  The
 // exponentials of a tile start against the STALE reference maximum as soon as the scores are in registers; the
@@ -122,7 +123,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t k_full = b0 + 32, k_empty = b0 + 48;
   const uint32_t v_full = b0 + 64, v_empty = b0 + 80;
   const uint32_t s_full = b0 + 96, p_full = b0 + 112, o_full = b0 + 128, p_full2 = b0 + 144;
-  const uint32_t s_full2 = b0 + 160;
+  const uint32_t s_cons = b0 + 160;   // SPLIT_S: S_t(j) is in the softmax warps' registers (4 arrivals)
   const uint32_t p_part = b0 + 176;   // [PSPLIT][2 tiles]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
 
@@ -145,7 +146,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(s_full + 8 * i, 1);
       mbar_init(p_full + 8 * i, 4);
       mbar_init(p_full2 + 8 * i, 4);
-      mbar_init(s_full2 + 8 * i, 1);
+      mbar_init(s_cons + 8 * i, 4);
       for (int q = 0; q < 4; ++q) mbar_init(p_part + 8 * (q * 2 + i), 4);
       mbar_init(o_full + 8 * i, 1);
     }
@@ -215,57 +216,86 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
    } else if (warp == 9) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // The WHOLE warp walks the loop (warp-uniform control flow and operands) and one elected lane issues each group
+    // of tcgen05 instructions.  Written as `if (lane == 0) { loop }` the same code kept every descriptor in a
+    // per-thread register inside a divergent region, and ptxas wrapped each UTCHMMA in four R2UR moves plus an
+    // ELECT / BRA.U.ANY loop: ~89 clk of issue per 64-clk MMA, measured as an MMA warp that never waits on a barrier
+    // (profiles/r2_attn_issue_bound.md) — the kernel was issue-bound, not softmax-bound.  With uniform operands the
+    // descriptors live in uniform registers and a group of eight MMAs is eight back-to-back UTCHMMA.
+    {
       constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kKT, false, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16(kQT, kHD, false, !V_TRANS);
       uint32_t item_ph = 0;
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0;
       uint32_t pph[2] = {0, 0};
+      uint32_t cph[2] = {0, 0};
       const uint32_t tS[2] = {tmem_base, tmem_base + 128};
       const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
 
       constexpr uint32_t idesc_qk64 = make_idesc_bf16(kQT, 64, false, false);
-      // S_t = Q_t K^T, committed to s_full (and, when split, first to s_full for columns 0..63 then to
-      // s_full2 for columns 64..127)
-      auto mma_s = [&](int t, int kstage) {
+      // S_t = Q_t K^T, committed to s_full; `release_q` / `release_k`: also commit the Q tile / K stage back to the
+      // producer.  SPLIT_S issues it as two N = 64 halves (see the main loop): half 1 = score columns 64..127 = K rows
+      // 64..127 of the stage, half 0 = columns 0..63; only the half issued last commits.
+      auto mma_s_half = [&](int t, int kstage, int half, bool commit, bool release_q, bool release_k) {
+        const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sQ + t * kTile));
+        const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sK + kstage * kTile)) + ((half * 64 * 128) >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kHD / 16; ++k) {
+            const uint32_t off = ((k >> 2) * kHalf + (k & 3) * 32) >> 4;
+            umma_ss(tS[t] + half * 64, ad + off, bd + off, idesc_qk64, k != 0);
+          }
+          if (commit) umma_commit(s_full + 8 * t);
+          if (release_q) umma_commit(q_empty + 8 * t);
+          if (release_k) umma_commit(k_empty + 8 * kstage);
+        }
+        __syncwarp();
+      };
+      auto mma_s = [&](int t, int kstage, bool release_q, bool release_k) {
+        if (SPLIT_S) {
+          mma_s_half(t, kstage, 1, false, false, false);
+          mma_s_half(t, kstage, 0, true, release_q, release_k);
+          return;
+        }
         // descriptors differ only in the 14-bit start-address field: build once, add (byte offset >> 4)
         const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sQ + t * kTile));
         const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sK + kstage * kTile));
-        if (SPLIT_S) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-#pragma unroll
-            for (int k = 0; k < kHD / 16; ++k) {
-              const uint32_t off = ((k >> 2) * kHalf + (k & 3) * 32) >> 4;
-              umma_ss(tS[t] + half * 64, ad + off, bd + off + ((half * 64 * 128) >> 4), idesc_qk64, k != 0);
-            }
-            umma_commit((half == 0 ? s_full : s_full2) + 8 * t);
-          }
-        } else {
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kHD / 16; ++k) {
             const uint32_t off = ((k >> 2) * kHalf + (k & 3) * 32) >> 4;
             umma_ss(tS[t], ad + off, bd + off, idesc_qk, k != 0);
           }
           umma_commit(s_full + 8 * t);
+          if (release_q) umma_commit(q_empty + 8 * t);
+          if (release_k) umma_commit(k_empty + 8 * kstage);
         }
+        __syncwarp();
       };
       // PV in two K-halves: the first half (kv rows 0..63) is issued as soon as the softmax warps have
-      // published P[:, 0:64], overlapping the exponentials of the second half.
-      auto mma_pv = [&](int t, int vstage, bool first, uint32_t parity) {
+      // published P[:, 0:64], overlapping the exponentials of the second half.  `done_bar` (0 = none) is committed
+      // after the last part: o_full on the last kv tile; `release_v`: commit the V stage back to the producer.
+      auto mma_pv = [&](int t, int vstage, bool first, uint32_t parity, uint32_t done_bar, bool release_v) {
         const uint32_t b = smem_u32(sV + vstage * kTile);
         const uint64_t bd0 = V_TRANS ? make_desc_kmajor_sw128(b) : make_desc_mnmajor_sw128(b, kHalf, 1024);
 #pragma unroll
         for (int part = 0; part < PSPLIT; ++part) {
           mbar_wait(p_part + 8 * (part * 2 + t), parity);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kKT / 16 / PSPLIT; ++kk) {
-            const int k = part * (kKT / 16 / PSPLIT) + kk;
-            const uint32_t off = V_TRANS ? (((k >> 2) * kHalf + (k & 3) * 32) >> 4) : ((k * 16 * 128) >> 4);
-            umma_ts(tO[t], tS[t] + k * 8, bd0 + off, idesc_pv, (!first || k != 0));
+            for (int kk = 0; kk < kKT / 16 / PSPLIT; ++kk) {
+              const int k = part * (kKT / 16 / PSPLIT) + kk;
+              const uint32_t off = V_TRANS ? (((k >> 2) * kHalf + (k & 3) * 32) >> 4) : ((k * 16 * 128) >> 4);
+              umma_ts(tO[t], tS[t] + k * 8, bd0 + off, idesc_pv, (!first || k != 0));
+            }
+            if (part == PSPLIT - 1) {
+              if (done_bar != 0) umma_commit(done_bar);
+              if (release_v) umma_commit(v_empty + 8 * vstage);
+            }
           }
+          __syncwarp();
         }
       };
 
@@ -274,41 +304,61 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(q_full + 0, item_ph);
         mbar_wait(k_full + 8 * ks, kph);
         tc_fence_after();
-        mma_s(0, ks);
-        if (n_kv == 1) umma_commit(q_empty + 0);
+        mma_s(0, ks, n_kv == 1, false);
         mbar_wait(q_full + 8, item_ph);
         tc_fence_after();
-        mma_s(1, ks);
-        if (n_kv == 1) umma_commit(q_empty + 8);
-        umma_commit(k_empty + 8 * ks);
+        mma_s(1, ks, n_kv == 1, true);
         if (++ks == kKVStages) { ks = 0; kph ^= 1; }
 
         for (int j = 0; j < n_kv; ++j) {
           const bool last = (j + 1 == n_kv);
+          if (SPLIT_S) {
+            // P_t(j) (bf16) aliases only score columns 0..63, so columns 64..127 of S_t are free as soon as the softmax
+            // warps hold S_t(j) in registers (s_cons).  The second half of S_t(j+1) is issued right then — it runs on the
+            // tensor pipe while the exponentials of S_t(j) are computed — and only the first half (256 clk instead of
+            // 512) stays on the tile's S -> softmax -> PV -> S dependency chain, after PV_t(j).
+            if (!last) {
+              mbar_wait(k_full + 8 * ks, kph);
+              mbar_wait(s_cons + 0, cph[0]);
+              cph[0] ^= 1;
+              tc_fence_after();
+              mma_s_half(0, ks, 1, false, false, false);
+            }
+            mbar_wait(v_full + 8 * vs, vph);
+            mma_pv(0, vs, j == 0, pph[0], last ? o_full + 0 : 0u, false);
+            pph[0] ^= 1;
+            if (!last) {
+              mma_s_half(0, ks, 0, true, j + 2 == n_kv, false);
+              mbar_wait(s_cons + 8, cph[1]);
+              cph[1] ^= 1;
+              tc_fence_after();
+              mma_s_half(1, ks, 1, false, false, false);
+            }
+            mma_pv(1, vs, j == 0, pph[1], last ? o_full + 8 : 0u, true);
+            pph[1] ^= 1;
+            if (++vs == kKVStages) { vs = 0; vph ^= 1; }
+            if (!last) {
+              mma_s_half(1, ks, 0, true, j + 2 == n_kv, true);
+              if (++ks == kKVStages) { ks = 0; kph ^= 1; }
+            }
+            continue;
+          }
           // ---- tile 0: O0 += P0(j) V_j ; then S0(j+1)
           mbar_wait(v_full + 8 * vs, vph);
-          mma_pv(0, vs, j == 0, pph[0]);
+          mma_pv(0, vs, j == 0, pph[0], last ? o_full + 0 : 0u, false);
           pph[0] ^= 1;
           if (!last) {
             mbar_wait(k_full + 8 * ks, kph);
             tc_fence_after();
-            mma_s(0, ks);
-            if (j + 2 == n_kv) umma_commit(q_empty + 0);
-          } else {
-            umma_commit(o_full + 0);
+            mma_s(0, ks, j + 2 == n_kv, false);
           }
           // ---- tile 1: O1 += P1(j) V_j ; then S1(j+1)
-          mma_pv(1, vs, j == 0, pph[1]);
+          mma_pv(1, vs, j == 0, pph[1], last ? o_full + 8 : 0u, true);
           pph[1] ^= 1;
-          umma_commit(v_empty + 8 * vs);
           if (++vs == kKVStages) { vs = 0; vph ^= 1; }
           if (!last) {
-            mma_s(1, ks);
-            if (j + 2 == n_kv) umma_commit(q_empty + 8);
-            umma_commit(k_empty + 8 * ks);
+            mma_s(1, ks, j + 2 == n_kv, true);
             if (++ks == kKVStages) { ks = 0; kph ^= 1; }
-          } else {
-            umma_commit(o_full + 8);
           }
         }
       }
@@ -592,14 +642,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         tmem_ld32(tS + 0, s + 0);
         tmem_ld32(tS + 32, s + 32);
-        if (SPLIT_S) {
-          mbar_wait(s_full2 + 8 * t, sph);
-          tc_fence_after();
-        }
         sph ^= 1;
         tmem_ld32(tS + 64, s + 64);
         tmem_ld32(tS + 96, s + 96);
         tmem_ld_wait();
+        if (SPLIT_S && j + 1 < n_kv) {     // the scores are in registers: columns 64..127 of S_t may be overwritten
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_cons + 8 * t);
+        }
         if (j == n_kv - 1 && rem < kKT) {
 #pragma unroll
           for (int c = 0; c < 128; ++c)
@@ -790,7 +841,8 @@ static int attn_fwd_impl(const void* q, long long ldq, const void* k, long long 
     lrc = v_transposed ? launch(attn_fwd_kernel<true, 0, false, 2, 2>) : launch(attn_fwd_kernel<false, 0, false, 2, 2>);
   } else if (emu == 3 || split_s) {            // experimental variants, natural-V layout only
     VCOF_REQUIRE(!v_transposed, "vcof_attn_fwd: tuning variants support the natural V layout only");
-    if (emu == 3) lrc = launch(attn_fwd_kernel<false, 3, false, 2>);
+    if (emu == 3 && split_s) lrc = launch(attn_fwd_kernel<false, 3, true, 2>);
+    else if (emu == 3) lrc = launch(attn_fwd_kernel<false, 3, false, 2>);
     else lrc = launch(attn_fwd_kernel<false, 0, true, 2>);
   } else if (v_transposed) {
     lrc = psplit == 4 ? launch(attn_fwd_kernel<true, 0, false, 4>) : launch(attn_fwd_kernel<true, 0, false, 2>);

@@ -75,8 +75,14 @@ struct ConvArgs {
 
 // Epilogue of ONE output position (this thread's TMEM lane, n_end accumulator columns starting at t_row):
 // bias (+ residual, clamp) -> bf16 store, and optionally the next layer's RMS_norm + SiLU as a second output.
-__device__ __forceinline__ void conv_epilogue_row(const ConvArgs& p, const float* sBias, const float* sGamma,
-                                                  uint32_t t_row, int t, int h, int w, int n0, int n_end) {
+// `release_bar` (0 = none): mbarrier on which the accumulator is handed back to the MMA warp.  Returns true when the
+// function arrived on it itself — on the path that keeps the whole channel row in registers this happens right after
+// the last tcgen05.ld, BEFORE the activation sweep and the stores, so the next tile's MMAs into this accumulator
+// overlap the epilogue's long tail (the fused RMS_norm + SiLU epilogue of a 96-channel row is ~2500 clk; released
+// only at its end it stalled the line kernel's MMA warp for ~5000 clk per 31 000-clk work item).
+__device__ __forceinline__ bool conv_epilogue_row(const ConvArgs& p, const float* sBias, const float* sGamma,
+                                                  uint32_t t_row, int t, int h, int w, int n0, int n_end,
+                                                  uint32_t release_bar = 0) {
   const bool ok = (h < p.H_out) && (w < p.W_out);
   const long long pos_row = (long long)(h * p.oh_mul + p.oh_add) * p.Ws + (w * p.ow_mul + p.ow_add);
   const int frame = t * p.ot_mul + p.ot_add;
@@ -156,7 +162,11 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvArgs& p, const float
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float a = bf16_round(v[q * 4 + e]) * inv * gg[e];
-        v[q * 4 + e] = __fdividef(a, 1.f + __expf(-a));
+        // silu(a) = a * sigmoid(a) = a * (0.5 + 0.5 * tanh(a / 2)): one MUFU op (tanh.approx, rel. error 2^-11, well
+        // under the bf16 store's 2^-9) instead of the two of a / (1 + exp(-a))
+        float th;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * a));
+        v[q * 4 + e] = a * fmaf(0.5f, th, 0.5f);
       }
     }
     (void)cnt;
@@ -190,6 +200,11 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvArgs& p, const float
         }
       }
     }
+    if (release_bar != 0) {          // every accumulator column of this row is in registers now (warp-uniform branch)
+      tc_fence_before();
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(release_bar);
+    }
     const float inv = sqrtf(float(p.n_store)) / fmaxf(sqrtf(sq), 1e-12f);
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci) {
@@ -198,6 +213,7 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvArgs& p, const float
         store(p.act_out + off[ci], v[ci], cnt[ci]);
       }
     }
+    return release_bar != 0;
   } else {
     // wider rows: second sweep over TMEM instead of 384 live registers
     float sq = 0.f;
@@ -225,6 +241,7 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvArgs& p, const float
       store(p.act_out + off, v, cnt);
     }
   }
+  return false;
 }
 
 __global__ void __launch_bounds__(kCvThreads, 1)
@@ -297,7 +314,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   };
 
   if (warp == 4 || (warp == 6 && p.producers == 2)) {
-    if (lane == 0) {
+    // All lanes walk the loop (warp-uniform operands -> uniform registers), one elected lane issues: see gemm_sm100.cu.
+    {
       const bool load_a = warp == 4;
       const bool load_b = (warp == 6) || (p.producers == 1);
       const uint32_t tx = p.tgroup * ((load_a ? a_bytes : 0) + (load_b ? b_bytes : 0));
@@ -320,23 +338,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const int cch = tp.c_base + cc * p.kc;
             const int slice = (g * p.cin_chunks + cc) * p.tgroup;
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            mbar_expect_tx(bar, tx);
-            // [kc c, 16 w, 1, 8 h, tgroup t] -> tgroup consecutive 128-row K-major tiles
-            if (load_a) tma_load_5d(st, &tmX, bar, cch, cw, tp.p, chh, ct);
-            if (load_b) {
-              tma_load_3d(st + b_off_bytes, &tmW, bar, 0, n0, slice);
-              if (nsub == 2) tma_load_3d(st + b_off_bytes + b_sub_bytes, &tmW, bar, 0, n0 + n_sub, slice);
+            if (elect_one()) {
+              mbar_expect_tx(bar, tx);
+              // [kc c, 16 w, 1, 8 h, tgroup t] -> tgroup consecutive 128-row K-major tiles
+              if (load_a) tma_load_5d(st, &tmX, bar, cch, cw, tp.p, chh, ct);
+              if (load_b) {
+                tma_load_3d(st + b_off_bytes, &tmW, bar, 0, n0, slice);
+                if (nsub == 2) tma_load_3d(st + b_off_bytes + b_sub_bytes, &tmW, bar, 0, n0 + n_sub, slice);
+              }
             }
+            __syncwarp();
             if (++s == kCvStages) { s = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      // Single-lane code is latency-bound (one dependent ALU op ~ 5 clk) and sits on the ring's slot cycle, so the
-      // issue loop is descriptor += constant only: all smem addresses are < 256 KB and 16-byte multiples, hence an
-      // offset is a plain add on the descriptor's 14-bit address field.
+    {
+      // The issue loop is descriptor += constant only: all smem addresses are < 256 KB and 16-byte multiples, hence an
+      // offset is a plain add on the descriptor's 14-bit address field (uniform-register arithmetic: the whole warp
+      // walks the loop, one elected lane issues).
       const uint32_t idesc = make_idesc_bf16(128, n_sub, false, false);
       const bool wide = p.kc == 64;
       const uint64_t dflags = wide ? (kDescVersion1 | kDescSwizzle128 | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 16))
@@ -375,12 +396,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const uint64_t a_desc = desc0 + uint32_t(s) * stage_step;
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          if (wide) issue_stage(std::integral_constant<int, 4>{}, a_desc, d_tmem, k == 0);
-          else issue_stage(std::integral_constant<int, 2>{}, a_desc, d_tmem, k == 0);
-          umma_commit(bar_empty + 8 * s);
+          if (elect_one()) {
+            if (wide) issue_stage(std::integral_constant<int, 4>{}, a_desc, d_tmem, k == 0);
+            else issue_stage(std::integral_constant<int, 2>{}, a_desc, d_tmem, k == 0);
+            umma_commit(bar_empty + 8 * s);
+            if (k == num_k - 1) umma_commit(bar_tfull + 8 * acc);
+          }
+          __syncwarp();
           if (++s == kCvStages) { s = 0; ph ^= 1; }
         }
-        umma_commit(bar_tfull + 8 * acc);
       }
     }
   } else if (warp < 4) {
@@ -394,11 +418,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tc_fence_after();
       const int r = warp * 32 + lane;
       const int h = h0 + (r >> 4), w = w0 + (r & 15);
-      conv_epilogue_row(p, sBias, sGamma, tmem_base + ((warp * 32u) << 16) + acc * 256, t, h, w, n0,
-                        min(p.n_tile, p.n_total - n0));
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      const bool released = conv_epilogue_row(p, sBias, sGamma, tmem_base + ((warp * 32u) << 16) + acc * 256, t, h, w,
+                                              n0, min(p.n_tile, p.n_total - n0), bar_tempty + 8 * acc);
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      }
     }
   }
 
@@ -497,7 +523,7 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   };
 
   if (warp == 4) {
-    if (lane == 0) {            // ---- line producer ----
+    {                           // ---- line producer (all lanes walk the loop, one elected lane issues) ----
       int s = 0;
       uint32_t ph = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -509,15 +535,18 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             for (int r = 0; r < R + 2; ++r) {
               const uint32_t dst = smem_l + s * kLnBytes;
               mbar_wait(bar_lempty + 8 * s, ph ^ 1);
-              mbar_expect_tx(bar_lfull + 8 * s, kLnPix * 64);
-              tma_load_5d(dst, &tmX, bar_lfull + 8 * s, cc * 32, w0 - 1, 0, h0 - 1 + r, ct);
+              if (elect_one()) {
+                mbar_expect_tx(bar_lfull + 8 * s, kLnPix * 64);
+                tma_load_5d(dst, &tmX, bar_lfull + 8 * s, cc * 32, w0 - 1, 0, h0 - 1 + r, ct);
+              }
+              __syncwarp();
               if (++s == a.ring) { s = 0; ph ^= 1; }
             }
           }
       }
     }
   } else if (warp == 6) {
-    if (lane == 0) {            // ---- weight producer ----
+    {                           // ---- weight producer ----
       int b = 0;
       uint32_t ph = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -525,14 +554,17 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         decode(item, t, h0, w0, n0);
         for (int phase = 0; phase < phases; ++phase) {
           mbar_wait(bar_wempty + 8 * b, ph ^ 1);
-          mbar_expect_tx(bar_wfull + 8 * b, w_bytes);
-          tma_load_3d(smem_w + b * w_bytes, &tmW, bar_wfull + 8 * b, 0, n0, phase * 9);
+          if (elect_one()) {
+            mbar_expect_tx(bar_wfull + 8 * b, w_bytes);
+            tma_load_3d(smem_w + b * w_bytes, &tmW, bar_wfull + 8 * b, 0, n0, phase * 9);
+          }
+          __syncwarp();
           if (++b == 2) { b = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {            // ---- MMA issuer ----
+    {                           // ---- MMA issuer (all lanes walk the loop, one elected lane issues per line) ----
       const uint32_t idesc = make_idesc_bf16(128, p.n_tile, false, false);
       const uint64_t dflags = kDescVersion1 | kDescSwizzle64 | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 16);
       const uint64_t wdesc0 = dflags | uint64_t((smem_w & 0x3FFFF) >> 4);
@@ -547,31 +579,34 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (int r = 0; r < R + 2; ++r) {
             const uint64_t ldesc = ldesc0 + uint32_t(s) * (kLnBytes >> 4);
             mbar_wait(bar_lfull + 8 * s, lph);
-            tc_fence_after();
-#pragma unroll
-            for (int dh = 0; dh < 3; ++dh) {
-              const int j = r - dh;                              // output row this line feeds through vertical tap dh
-              if (j < 0 || j >= R) continue;
-              const bool first = (phase == 0) && (dh == 0);      // first MMA ever into accumulator j of this item
-              if (first) {
-                mbar_wait(bar_tempty + 8 * j, (it & 1) ^ 1);     // epilogue of the previous item has drained row j
-                tc_fence_after();
-              }
-              const uint32_t d_tmem = tmem_base + j * acc_stride;
-#pragma unroll
-              for (int dw = 0; dw < 3; ++dw) {
-                // horizontal tap = the same line read dw pixels (64-byte rows) further in
-                const uint64_t ad = ldesc + dw * 4;
-                const uint64_t bd = wdesc + (dh * 3 + dw) * w_tile;
-                umma_ss(d_tmem, ad, bd, idesc, !(first && dw == 0));
-                umma_ss(d_tmem, ad + 2, bd + 2, idesc, 1);
-              }
-              if (phase == phases - 1 && dh == 2) umma_commit(bar_tfull + 8 * j);   // row j is complete
+            if (phase == 0) {
+              // first MMA ever into accumulator j = r (through dh = 0): the epilogue of the previous item has drained it
+              if (r < R) mbar_wait(bar_tempty + 8 * r, (it & 1) ^ 1);
             }
-            umma_commit(bar_lempty + 8 * s);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int dh = 0; dh < 3; ++dh) {
+                const int j = r - dh;                              // output row this line feeds through vertical tap dh
+                if (j < 0 || j >= R) continue;
+                const bool first = (phase == 0) && (dh == 0);      // first MMA ever into accumulator j of this item
+                const uint32_t d_tmem = tmem_base + j * acc_stride;
+#pragma unroll
+                for (int dw = 0; dw < 3; ++dw) {
+                  // horizontal tap = the same line read dw pixels (64-byte rows) further in
+                  const uint64_t ad = ldesc + dw * 4;
+                  const uint64_t bd = wdesc + (dh * 3 + dw) * w_tile;
+                  umma_ss(d_tmem, ad, bd, idesc, !(first && dw == 0));
+                  umma_ss(d_tmem, ad + 2, bd + 2, idesc, 1);
+                }
+                if (phase == phases - 1 && dh == 2) umma_commit(bar_tfull + 8 * j);   // row j is complete
+              }
+              umma_commit(bar_lempty + 8 * s);
+              if (r == R + 1) umma_commit(bar_wempty + 8 * b);
+            }
+            __syncwarp();
             if (++s == a.ring) { s = 0; lph ^= 1; }
           }
-          umma_commit(bar_wempty + 8 * b);
           if (++b == 2) { b = 0; wph ^= 1; }
         }
       }
@@ -586,11 +621,15 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int j = 0; j < R; ++j) {
         mbar_wait(bar_tfull + 8 * j, it & 1);
         tc_fence_after();
+        bool released = false;
         if (h0 + j < p.H_out)
-          conv_epilogue_row(p, sBias, sGamma, tmem_base + ((warp * 32u) << 16) + j * acc_stride, t, h0 + j, w, n0, n_end);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * j);
+          released = conv_epilogue_row(p, sBias, sGamma, tmem_base + ((warp * 32u) << 16) + j * acc_stride, t, h0 + j, w,
+                                       n0, n_end, bar_tempty + 8 * j);
+        if (!released) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * j);
+        }
       }
     }
   }

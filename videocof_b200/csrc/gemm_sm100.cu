@@ -279,7 +279,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 4 || (warp == 6 && p.producers == 2)) {
     // ---------------- TMA producer(s) ----------------
-    if (lane == 0) {
+    // Producer and MMA warps run their loops with ALL lanes (warp-uniform control flow and operands) and elect one lane
+    // for the issue: inside an `if (lane == 0)` region ptxas keeps every operand in per-thread registers and wraps each
+    // UTMALDG / UTCHMMA in R2UR moves plus an ELECT / BRA.U.ANY loop (profiles/r2_attn_issue_bound.md); with uniform
+    // operands the descriptors and coordinates live in uniform registers and the issue is one instruction.
+    {
       const bool load_a = warp == 4;
       const bool load_b = (warp == 6) || (p.producers == 1);
       const uint32_t tx = (load_a ? Cfg::kABytes : 0) + (load_b ? Cfg::kBBytes : 0);
@@ -290,18 +294,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          mbar_expect_tx(bar_full + 8 * s, tx);
-          if (load_a)
-            tma_load_2d(smem_u32(sA + s * Cfg::kABytes), &tmA, bar_full + 8 * s, kb * kBK, m_blk * kBM);
-          if (load_b)
-            tma_load_2d(smem_u32(sB + s * Cfg::kBBytes), &tmB, bar_full + 8 * s, kb * kBK, n_blk * BN);
+          if (elect_one()) {
+            mbar_expect_tx(bar_full + 8 * s, tx);
+            if (load_a)
+              tma_load_2d(smem_u32(sA + s * Cfg::kABytes), &tmA, bar_full + 8 * s, kb * kBK, m_blk * kBM);
+            if (load_b)
+              tma_load_2d(smem_u32(sB + s * Cfg::kBBytes), &tmB, bar_full + 8 * s, kb * kBK, n_blk * BN);
+          }
+          __syncwarp();
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 5) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, false, false);
       int s = 0;
       uint32_t ph = 0;
@@ -313,20 +320,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          // descriptors before the wait: single-lane instructions after the wake-up sit on the ring's slot cycle
           const uint64_t a_desc = make_desc_kmajor_sw128(smem_u32(sA + s * Cfg::kABytes));
           const uint64_t b_desc = make_desc_kmajor_sw128(smem_u32(sB + s * Cfg::kBBytes));
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // +32 bytes per K=16 step = +2 in the descriptor's 16-byte address field
-            umma_ss(d_tmem, a_desc + k * 2, b_desc + k * 2, idesc, (kb | k) != 0);
+            for (int k = 0; k < kBK / 16; ++k) {
+              // +32 bytes per K=16 step = +2 in the descriptor's 16-byte address field
+              umma_ss(d_tmem, a_desc + k * 2, b_desc + k * 2, idesc, (kb | k) != 0);
+            }
+            umma_commit(bar_empty + 8 * s);
+            if (kb == num_kb - 1) umma_commit(bar_tfull + 8 * acc);
           }
-          umma_commit(bar_empty + 8 * s);
+          __syncwarp();
           if (++s == S) { s = 0; ph ^= 1; }
         }
-        umma_commit(bar_tfull + 8 * acc);
       }
     }
   } else if (warp < 4) {
@@ -357,12 +366,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------
-// CTA-pair variant (cta_group::2), 256 x 256 tiles per pair.  EXPERIMENTAL, opt-in with VCOF_GEMM_2CTA=1 — written
-// at the end of round 1 and not yet validated on hardware: the single-CTA kernel needs 48 KB of
+// CTA-pair variant (cta_group::2), 256 x 256 tiles per pair; default for the plain bias epilogue (see vcof_gemm_bf16).
+// The single-CTA kernel needs 48 KB of
 // operands per 512-clock k-block (96 B/clk/SM) against a measured feed of ~77 B/clk/SM; here each CTA stages its own
 // 128 rows of A and only HALF of the 256 rows of B (32 KB per k-block, 64 B/clk/SM), six stages deep.
 //   rank 0 (leader): its MMA lane issues tcgen05.mma.cta_group::2 (M = 256: 128 TMEM lanes in each CTA) after
-//     waiting on ITS full[s], which counts one arrival per CTA plus the TMA bytes of both;
+//     waiting on ITS full[s], which counts the leader's arrive.expect_tx plus the TMA bytes of both CTAs;
 //   both ranks: TMA producer (own A rows, own half of B), completion bytes go to the leader's full[s];
 //     slot release = the leader's commit, multicast to empty[s] of both CTAs; accumulator-ready likewise (tfull);
 //   both ranks: four epilogue warps drain their own 128 lanes; accumulator-free arrivals all go to the leader's
@@ -409,7 +418,7 @@ gemm2cta_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 5) {
     if (lane == 0) {
       for (int i = 0; i < S; ++i) {
-        mbar_init(bar_full + 8 * i, 2);
+        mbar_init(bar_full + 8 * i, 1);            // the leader's arrive.expect_tx; both CTAs' TMA bytes complete on it
         mbar_init(bar_empty + 8 * i, 1);
       }
       for (int i = 0; i < 2; ++i) {
@@ -436,7 +445,7 @@ gemm2cta_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   if (warp == 4) {
     // ---------------- TMA producer (both CTAs) ----------------
-    if (lane == 0) {
+    {
       const uint32_t full_leader = mapa_shared(bar_full, 0);
       int s = 0;
       uint32_t ph = 0;
@@ -447,17 +456,24 @@ gemm2cta_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int row_b = n_blk * BN + int(rank) * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * Cfg::kStageBytes);   // arrival 1 of 2 + bytes of both CTAs
-          else mbar_arrive_cluster(full_leader + 8 * s);                          // arrival 2 of 2
-          tma_load_2d_pair(smem_u32(sA + s * Cfg::kABytes), &tmA, full_leader + 8 * s, kb * kBK, row_a);
-          tma_load_2d_pair(smem_u32(sB + s * Cfg::kBBytes), &tmB, full_leader + 8 * s, kb * kBK, row_b);
+          if (elect_one()) {
+            // Only the leader arrives (with the bytes of BOTH CTAs).  The peer's boxes may complete on the leader's
+            // barrier before that arrive — a transiently negative tx-count is legal, the phase cannot complete while
+            // the arrival is pending — and the peer cannot run a phase ahead: it reloads slot s only after the
+            // leader's multicast commit on empty[s].  (The first version made the peer arrive remotely with
+            // .release.cluster: a GPU-scope fence per stage, 1460 clk per k-block = exactly half speed.)
+            if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(smem_u32(sA + s * Cfg::kABytes), &tmA, full_leader + 8 * s, kb * kBK, row_a);
+            tma_load_2d_pair(smem_u32(sB + s * Cfg::kBBytes), &tmB, full_leader + 8 * s, kb * kBK, row_b);
+          }
+          __syncwarp();
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 5) {
     // ---------------- MMA issuer (leader CTA only) ----------------
-    if (lane == 0 && leader) {
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * kBM, BN, false, false);
       int s = 0;
       uint32_t ph = 0;
@@ -473,12 +489,15 @@ gemm2cta_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const uint64_t b_desc = make_desc_kmajor_sw128(smem_u32(sB + s * Cfg::kBBytes));
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) umma_ss_pair(d_tmem, a_desc + k * 2, b_desc + k * 2, idesc, (kb | k) != 0);
-          umma_commit_pair(bar_empty + 8 * s);
+            for (int k = 0; k < kBK / 16; ++k) umma_ss_pair(d_tmem, a_desc + k * 2, b_desc + k * 2, idesc, (kb | k) != 0);
+            umma_commit_pair(bar_empty + 8 * s);
+            if (kb == num_kb - 1) umma_commit_pair(bar_tfull + 8 * acc);
+          }
+          __syncwarp();
           if (++s == S) { s = 0; ph ^= 1; }
         }
-        umma_commit_pair(bar_tfull + 8 * acc);
       }
     }
   } else if (warp < 4) {
@@ -648,12 +667,19 @@ extern "C" int vcof_gemm_bf16(const void* a, long long lda, const void* w, long 
     args.producers = producers;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static const bool pair_mode = [] {
+  // CTA-pair kernel (cta_group::2, 256 x 256 tiles).  Measured on B200 (profiles/r2_gpurun9_gemm_2cta_fixed.log):
+  // bias epilogue 75600 x 5120 x 5120: 1540 TFLOP/s against 1453 for the single-CTA kernel (cuBLAS: 1507); the GELU and
+  // gate + fp32-residual epilogues are 1-8 % SLOWER in pairs (two coupled epilogues per accumulator), so the default
+  // ("auto") uses pairs for the plain bias epilogue only.  VCOF_GEMM_2CTA=0: never, =1: all three epilogues.
+  static const int pair_mode = [] {
     const char* e = getenv("VCOF_GEMM_2CTA");
-    return e != nullptr && e[0] == '1';
+    return e == nullptr ? 2 : (e[0] == '1' ? 1 : (e[0] == '0' ? 0 : 2));
   }();
-  if (pair_mode && !narrow && N >= 256 && M >= 256 && epilogue <= VCOF_EPI_BIAS_GATE_RES_F32) {
-    // experimental CTA-pair kernel: B box is this CTA's 128-row half of the 256-row tile
+  const bool pair_ok = !narrow && N >= 256 && M >= 256 &&
+                       ((pair_mode == 1 && epilogue <= VCOF_EPI_BIAS_GATE_RES_F32) ||
+                        (pair_mode == 2 && epilogue == VCOF_EPI_BIAS_BF16));
+  if (pair_ok) {
+    // B box is this CTA's 128-row half of the 256-row tile
     rc = make_tmap_2d_bf16(&tmB, w, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, kBK, 128);
     if (rc) return rc;
     return dispatch_epi_2cta(epilogue, tmA, tmB, args, st);

@@ -273,8 +273,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier that may live in the peer CTA.  No explicit `.release.cluster`: ptxas turns that qualifier into
+// MEMBAR.ALL.GPU + ERRBAR in front of every arrive (~1400 clk each, profiles/r2_gemm2cta_ncu_summary.txt); what the
+// arrive orders here are tcgen05 operations, which tcgen05.wait / tcgen05.fence::before_thread_sync already cover.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA tile load into THIS CTA's shared memory whose completion bytes are counted on a barrier that may live in the
 // peer CTA of the pair (`bar_cluster` is a shared::cluster address)

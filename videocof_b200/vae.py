@@ -424,16 +424,18 @@ def conv_causal(x, conv, residual=None, clamp=0.0, n_store=None, act_norm=None, 
 
 
 def _use_lines(conv):
-    """Which kernel runs a stride-1 3x3(x3) layer.  Default ("auto"): the line-resident kernel for layers of up to 128
-    output channels (one channel pass, fused norm kept: 1.3-1.9x faster at 96 channels, profiles/
-    r1_gpurun36_final_validation_lines.log), the tap-streaming kernel for wider ones (several passes would re-stream the
-    lines and drop the fused RMS_norm+SiLU).  VCOF_CONV_LINES=1 / 0 forces it on for every eligible layer / off."""
+    """Which kernel runs a stride-1 3x3(x3) layer.  Default ("auto"): the line-resident kernel for EVERY such layer.
+    Round 1 kept the 192- / 384-channel layers on the tap-streaming kernel (several channel passes drop the fused
+    RMS_norm+SiLU); since the issue loops became warp-uniform (round 2) the line kernel runs those layers at
+    1.1-1.2 PFLOP/s against 0.95-1.0 and wins even with the separate norm pass (9 f x 720p decode 92.4 ms vs 97.2,
+    profiles/r2_gpurun7_vae_elect.json).  VCOF_CONV_LINES=0 forces the tap-streaming kernel, "narrow" restores the
+    round-1 rule (line kernel up to 128 output channels)."""
     mode = os.environ.get("VCOF_CONV_LINES", "auto")
-    if mode == "1":
-        return True
     if mode == "0":
         return False
-    return _pad16(conv.weight.shape[0]) <= 128
+    if mode == "narrow":
+        return _pad16(conv.weight.shape[0]) <= 128
+    return True
 
 
 def _conv_causal_lines(x, conv, kt, residual, clamp, n_store, act_norm, want_raw):
