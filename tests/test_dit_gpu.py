@@ -140,3 +140,23 @@ def test_cfg_skip_drops_the_unconditional_half():
         skipped = model(**args)
     assert torch.equal(skipped[0], skipped[1])
     assert torch.equal(skipped[1], full[1])
+
+
+def test_batched_cfg_forward_is_bit_identical_to_the_per_sample_loop(monkeypatch):
+    """Batch 2 (classifier-free guidance): tokens of both samples stacked along M (weights stream once per step) must
+    reproduce the per-sample loop bit for bit — the GEMM tiles of a row do not depend on how many rows follow it."""
+    ckw, shape, n_ctx, B = DIT_CASES["dit_tiny_b2"]
+    cfg = DiTConfig(**ckw)
+    params = make_dit_params(cfg, seed=11)
+    x, ctx, t = dit_inputs(shape, n_ctx, cfg.text_dim, B, seed=23)
+    f = shape[1]
+    seq_len = f * (shape[2] // 2) * (shape[3] // 2)
+    model = build_cuda_model(cfg, params)
+    args = dict(x=x.cuda().bfloat16(), t=t.cuda(), context=[c.cuda().bfloat16() for c in ctx], seq_len=seq_len + 3,
+                **ROPE_MODES["cot"](f, B))
+    with torch.no_grad():
+        monkeypatch.setenv("VCOF_DIT_BATCHED", "0")
+        loop = model(**args)
+        monkeypatch.setenv("VCOF_DIT_BATCHED", "1")
+        batched = model(**args)
+    assert torch.equal(loop, batched)

@@ -277,3 +277,21 @@ def test_push_exchange_forward_matches_single_rank(world, heads, monkeypatch):
     for key, bufs in shared.items():
         if isinstance(key, tuple) and key[0] == "buf":
             assert all(not torch.isnan(b.float()).any() for b in bufs), key
+
+
+@pytest.mark.parametrize("pad", [0, 5])
+def test_batched_forward_is_bit_identical_to_the_per_sample_loop(monkeypatch, pad):
+    """CFG batch 2 (pipeline_wan.py:700): the batch-aware forward stacks the samples' tokens along M so that the block
+    stack streams its weights once per step (WanAttentionBlock.run_batched); row-wise the arithmetic is unchanged, so
+    the output must equal the per-sample loop's (VCOF_DIT_BATCHED=0) bit for bit — also with a padded sequence."""
+    vcof_emulator.install_dit(monkeypatch)
+    cfg, params, x, ctx, t, f, L, B, _ = case("dit_tiny_b2")
+    assert B == 2
+    model = build_model(cfg, params)
+    args = dict(x=x.bfloat16(), t=t, context=[c.bfloat16() for c in ctx], seq_len=L + pad, **ROPE_MODES["cot"](f, B))
+    with torch.no_grad():
+        monkeypatch.setenv("VCOF_DIT_BATCHED", "0")
+        loop = model(**args)
+        monkeypatch.setenv("VCOF_DIT_BATCHED", "1")
+        batched = model(**args)
+    assert torch.equal(loop, batched)

@@ -109,9 +109,23 @@ rmsnorm_rope_kernel(bf16* __restrict__ x, long long ldx, const bf16* __restrict_
                     int row_offset, bf16* __restrict__ y, int cols_per_block, long long block_stride,
                     const __grid_constant__ ScatterPtrs dst) {
   __shared__ float scratch[kRmsThreads / 32];
+  // cos / sin of this row's rotation, one entry per complex pair of a head: every head of the row uses the same 64
+  // angles, so they are fetched from the table ONCE per row (first kRmsThreads lanes, published by the barrier inside
+  // block_sum) instead of once per pair per head (20 scattered 8-byte loads per thread: the kernel ran at 0.44 of the
+  // HBM rate inside a step, LSU-bound, not DRAM-bound)
+  __shared__ __align__(16) float2 s_cs[kRmsThreads];
   const long long row = blockIdx.x;
   uint4* xr = reinterpret_cast<uint4*>(x + row * ldx);
   const int nvec = C >> 3;
+  const long long g = (long long)row_offset + row;
+  const bool do_rope = (table != nullptr) && (g < (long long)F * H * W);
+  if (do_rope && threadIdx.x < (head_dim >> 1)) {
+    const int f = int(g / ((long long)H * W));
+    const int r = int(g % ((long long)H * W));
+    const int pi = threadIdx.x;
+    const int pos = (pi < n_t) ? tpos[f] : ((pi < n_t + n_h) ? r / W : r % W);
+    s_cs[pi] = __ldg(table + pos * (head_dim >> 1) + pi);
+  }
   uint4 v[kRmsMaxVec];
   float sq = 0.f;
 #pragma unroll
@@ -131,16 +145,6 @@ rmsnorm_rope_kernel(bf16* __restrict__ x, long long ldx, const bf16* __restrict_
   // the reference rounds the rsqrt factor to bf16 before the multiply (:229)
   const float rs = bf16_round(rsqrtf(ms + eps));
 
-  const long long g = (long long)row_offset + row;
-  const bool do_rope = (table != nullptr) && (g < (long long)F * H * W);
-  int tp = 0, hh = 0, ww = 0;
-  if (do_rope) {
-    const int f = int(g / ((long long)H * W));
-    const int r = int(g % ((long long)H * W));
-    hh = r / W;
-    ww = r % W;
-    tp = tpos[f];
-  }
 #pragma unroll
   for (int i = 0; i < kRmsMaxVec; ++i) {
     const int idx = threadIdx.x + i * kRmsThreads;
@@ -149,7 +153,14 @@ rmsnorm_rope_kernel(bf16* __restrict__ x, long long ldx, const bf16* __restrict_
       const uint4 wv = __ldg(reinterpret_cast<const uint4*>(weight) + idx);
       const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wv);
       uint32_t o[4];
-      const int pair0 = ((idx * 8) % head_dim) >> 1;  // first complex pair of this vector
+      const int pair0 = ((idx * 8) % head_dim) >> 1;  // first complex pair of this vector (a multiple of 4)
+      float2 csv[4];
+      if (do_rope) {
+        const float4 c01 = *reinterpret_cast<const float4*>(&s_cs[pair0]);
+        const float4 c23 = *reinterpret_cast<const float4*>(&s_cs[pair0 + 2]);
+        csv[0] = make_float2(c01.x, c01.y); csv[1] = make_float2(c01.z, c01.w);
+        csv[2] = make_float2(c23.x, c23.y); csv[3] = make_float2(c23.z, c23.w);
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = __bfloat1622float2(h[e]);
@@ -157,9 +168,7 @@ rmsnorm_rope_kernel(bf16* __restrict__ x, long long ldx, const bf16* __restrict_
         float yr = bf16_round(bf16_round(f.x * rs) * w.x);
         float yi = bf16_round(bf16_round(f.y * rs) * w.y);
         if (do_rope) {
-          const int pi = pair0 + e;
-          const int pos = (pi < n_t) ? tp : ((pi < n_t + n_h) ? hh : ww);
-          const float2 cs = __ldg(table + pos * (head_dim >> 1) + pi);
+          const float2 cs = csv[e];
           const float r0 = yr * cs.x - yi * cs.y;
           const float r1 = yr * cs.y + yi * cs.x;
           yr = r0;
@@ -337,7 +346,7 @@ static int rmsnorm_rope_launch(void* x, long long ldx, const void* weight, float
   VCOF_REQUIRE(C % 8 == 0 && C <= kRmsThreads * kRmsMaxVec * 8 && ldx % 8 == 0,
                "vcof_rmsnorm_rope: C=%d / ldx must be multiples of 8, C <= %d", C,
                kRmsThreads * kRmsMaxVec * 8);
-  VCOF_REQUIRE(head_dim % 8 == 0 && C % head_dim == 0, "vcof_rmsnorm_rope: bad head_dim %d",
+  VCOF_REQUIRE(head_dim % 8 == 0 && C % head_dim == 0 && head_dim <= 2 * kRmsThreads, "vcof_rmsnorm_rope: bad head_dim %d",
                head_dim);
   VCOF_REQUIRE(rope_table == nullptr || (tpos != nullptr && n_t + n_h <= head_dim / 2),
                "vcof_rmsnorm_rope: rope requested without positions");
@@ -387,7 +396,8 @@ extern "C" int vcof_rmsnorm_rope_scatter(const void* x, long long ldx, void* con
                "vcof_rmsnorm_rope_scatter: C=%d must split into %d blocks of a multiple of 8 columns", C, n_blocks);
   VCOF_REQUIRE(C % 8 == 0 && C <= kRmsThreads * kRmsMaxVec * 8 && ldx % 8 == 0,
                "vcof_rmsnorm_rope_scatter: C=%d / ldx must be multiples of 8, C <= %d", C, kRmsThreads * kRmsMaxVec * 8);
-  VCOF_REQUIRE(head_dim % 8 == 0 && C % head_dim == 0, "vcof_rmsnorm_rope_scatter: bad head_dim %d", head_dim);
+  VCOF_REQUIRE(head_dim % 8 == 0 && C % head_dim == 0 && head_dim <= 2 * kRmsThreads,
+               "vcof_rmsnorm_rope_scatter: bad head_dim %d", head_dim);
   VCOF_REQUIRE(rope_table == nullptr || (tpos != nullptr && n_t + n_h <= head_dim / 2),
                "vcof_rmsnorm_rope_scatter: rope requested without positions");
   rmsnorm_rope_kernel<true><<<L, kRmsThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(

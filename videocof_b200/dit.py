@@ -180,6 +180,52 @@ class WanAttentionBlock(nn.Module):
         ops.gemm(ws.h, self.ffn[2].weight, self.ffn[2].bias, "bias_gate_res", out=x, gate=e[5])
         return x
 
+    def run_batched(self, X, es, ctx, ropes, kv_lens, ws, rows):
+        """Batch-aware block (classifier-free guidance: the uncond + cond samples of one step, pipeline_wan.py:700).
+        X fp32 [B*rows, C]: the samples' residual streams stacked along M (updated in place); es[b] fp32 [6, C];
+        ctx bf16 [B*S, C] the samples' text contexts stacked; ropes / kv_lens per sample.
+
+        Every Linear whose epilogue is sample-independent runs as ONE GEMM over all B*rows tokens — q, k, v, the
+        cross-attention q / k / v / o and the first FFN Linear: the weights stream once per step instead of once per
+        sample — while what depends on the sample runs per row range: AdaLN modulation, RoPE (positions restart),
+        attention (keys of one sample), and the two gated residual GEMMs (per-sample gate vector).  Row-wise the
+        arithmetic is that of `run`, so the result is bit-identical to the per-sample loop."""
+        sa, ca = self.self_attn, self.cross_attn
+        n, hd = self.num_heads, self.dim // self.num_heads
+        B = len(es)
+        S = ctx.shape[0] // B
+        rng = [slice(b * rows, (b + 1) * rows) for b in range(B)]
+        for b in range(B):
+            ops.ln_modulate(X[rng[b]], None, None, es[b][0], es[b][1], self.eps, out=ws.a[rng[b]])
+        ops.gemm(ws.a, sa.q.weight, sa.q.bias, "bias", out=ws.q)
+        ops.gemm(ws.a, sa.k.weight, sa.k.bias, "bias", out=ws.k)
+        ops.gemm(ws.a, sa.v.weight, sa.v.bias, "bias", out=ws.v)
+        for b in range(B):
+            ops.rmsnorm_rope_(ws.q[rng[b]], sa.norm_q.weight, sa.eps, hd, ropes[b])
+            ops.rmsnorm_rope_(ws.k[rng[b]], sa.norm_k.weight, sa.eps, hd, ropes[b])
+            ops.attention(ws.q[rng[b]], ws.k[rng[b]], ws.v[rng[b]], n, kv_len=kv_lens[b], out=ws.a[rng[b]])
+        for b in range(B):
+            ops.gemm(ws.a[rng[b]], sa.o.weight, sa.o.bias, "bias_gate_res", out=X[rng[b]], gate=es[b][2])
+        if not self.cross_attn_norm:
+            raise NotImplementedError("cross_attn_norm=False is not on the VideoCoF path")
+        ops.ln_modulate(X, _f32_cached(self, "n3w", self.norm3.weight), _f32_cached(self, "n3b", self.norm3.bias),
+                        None, None, self.eps, out=ws.a)
+        ops.gemm(ws.a, ca.q.weight, ca.q.bias, "bias", out=ws.q)
+        ops.rmsnorm_rope_(ws.q, ca.norm_q.weight, ca.eps, hd, None)
+        kc = ops.gemm(ctx, ca.k.weight, ca.k.bias, "bias")
+        ops.rmsnorm_rope_(kc, ca.norm_k.weight, ca.eps, hd, None)
+        vc = ops.gemm(ctx, ca.v.weight, ca.v.bias, "bias")
+        for b in range(B):
+            cs = slice(b * S, (b + 1) * S)
+            ops.attention(ws.q[rng[b]], kc[cs], vc[cs], n, out=ws.a[rng[b]])
+        ops.gemm(ws.a, ca.o.weight, ca.o.bias, "bias_gate_res", out=X, gate=None)
+        for b in range(B):
+            ops.ln_modulate(X[rng[b]], None, None, es[b][3], es[b][4], self.eps, out=ws.a[rng[b]])
+        ops.gemm(ws.a, self.ffn[0].weight, self.ffn[0].bias, "bias_gelu", out=ws.h)
+        for b in range(B):
+            ops.gemm(ws.h[rng[b]], self.ffn[2].weight, self.ffn[2].bias, "bias_gate_res", out=X[rng[b]], gate=es[b][5])
+        return X
+
     def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens=None, dtype=torch.bfloat16,
                 t=0, frame_split_indices=None, ground_frame_indices=None):
         """Reference signature (:464-477): x [B,L,C], e [B,6,C] fp32, context [B,S,C]."""
@@ -547,6 +593,14 @@ class WanTransformer3DModel(nn.Module):
             self.should_calc = should_calc          # attribute the reference also exposes (:968-981)
         residuals = []
 
+        # Batch-aware path (single GPU, B >= 2 samples of one shape — the CFG pair of inference.py): the samples'
+        # tokens are stacked along M so that the block stack streams its weights once per step (run_batched).
+        shapes = {tuple(u.shape) for u in xs}
+        if (len(xs) >= 2 and P == 1 and len(shapes) == 1 and os.environ.get("VCOF_DIT_BATCHED", "1") != "0"
+                and not (tc is not None and not should_calc)):
+            return self._forward_batched(xs, t, context, seq_len, cond_flag, frame_split_indices,
+                                         ground_frame_indices, embeds, tc)
+
         for b, u in enumerate(xs):
             u = u.to(torch.bfloat16).contiguous()
             cin, F_, H_, W_ = u.shape
@@ -598,6 +652,52 @@ class WanTransformer3DModel(nn.Module):
                 tc.previous_residual_cond = stacked
             else:
                 tc.previous_residual_uncond = stacked
+        if tc is not None and cond_flag:
+            tc.cnt += 1
+            if tc.cnt == tc.num_steps:
+                tc.reset()
+        return torch.stack(outs)
+
+    def _forward_batched(self, xs, t, context, seq_len, cond_flag, frame_split_indices, ground_frame_indices, embeds, tc):
+        """`_forward` for B >= 2 same-shape samples on one GPU: tokens stacked [B*seq_len, C] (see run_batched)."""
+        dev = xs[0].device
+        C, B = self.dim, len(xs)
+        cin, F_, H_, W_ = xs[0].shape
+        f, h, w = F_, H_ // 2, W_ // 2
+        L = f * h * w
+        assert L <= seq_len, "seq_len shorter than the token count"          # (:906)
+        X = torch.zeros((B * seq_len, C), dtype=torch.float32, device=dev) if seq_len > L else \
+            torch.empty((B * seq_len, C), dtype=torch.float32, device=dev)
+        ctxs, ropes, mods = [], [], []
+        for b, u in enumerate(xs):
+            a = ops.patchify(u.to(torch.bfloat16).contiguous())
+            ops.gemm(a, self.patch_embedding.weight.view(C, -1), self.patch_embedding.bias, "bias_f32",
+                     out=X[b * seq_len:b * seq_len + L])
+            ctxs.append(self._text_embed(context[b]))
+            fs = frame_split_indices[b] if frame_split_indices is not None and b < len(frame_split_indices) else None
+            gr = ground_frame_indices[b] if (fs is not None and ground_frame_indices is not None
+                                             and b < len(ground_frame_indices)) else None
+            ropes.append(make_rope_spec(self.freqs, dev, f, h, w, fs, gr))
+            mods.append(self._mod_stack() + embeds[b][1])                    # [layers, 6, C] (:491)
+        ctx = torch.cat(ctxs, dim=0)
+        ori = X.clone() if tc is not None else None
+        ws = self._ws.get(dev, B * seq_len, C, self.ffn_dim)
+        for i, blk in enumerate(self.blocks):
+            blk.run_batched(X, [m[i] for m in mods], ctx, ropes, [L] * B, ws, seq_len)
+        if tc is not None:
+            res = (X - ori).view(B, seq_len, C)
+            res = res.cpu() if tc.offload else res
+            if cond_flag:
+                tc.previous_residual_cond = res
+            else:
+                tc.previous_residual_uncond = res
+        outs = []
+        for b in range(B):
+            e = embeds[b][0]
+            eh = (self.head.modulation.detach().to(torch.float32)[0] + e).contiguous()   # [2, C]
+            yb = ops.ln_modulate(X[b * seq_len:(b + 1) * seq_len], None, None, eh[0], eh[1], self.eps)
+            yo = ops.gemm(yb, self.head.head.weight, self.head.head.bias, "bias")
+            outs.append(ops.unpatchify(yo[:L], self.out_dim, f, H_, W_))
         if tc is not None and cond_flag:
             tc.cnt += 1
             if tc.cnt == tc.num_steps:
