@@ -153,7 +153,10 @@ rmsnorm_rope_kernel(bf16* __restrict__ x, long long ldx, const bf16* __restrict_
       const uint4 wv = __ldg(reinterpret_cast<const uint4*>(weight) + idx);
       const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wv);
       uint32_t o[4];
-      const int pair0 = ((idx * 8) % head_dim) >> 1;  // first complex pair of this vector (a multiple of 4)
+      // first complex pair of this vector (a multiple of 4); head dims are powers of two in practice: a mask instead
+      // of an integer modulo by a run-time value (a MUFU.RCP sequence per vector: the XU pipe was 53 % busy)
+      const int c0 = idx * 8;
+      const int pair0 = (((head_dim & (head_dim - 1)) == 0) ? (c0 & (head_dim - 1)) : (c0 % head_dim)) >> 1;
       float2 csv[4];
       if (do_rope) {
         const float4 c01 = *reinterpret_cast<const float4*>(&s_cs[pair0]);
