@@ -668,10 +668,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float m_new = fmaxf(m_ref, m_tile);
         const bool grow = (m_new - m_ref) * p.scale_log2 > kRescaleThresh;  // true at j == 0
         if (__any_sync(0xffffffffu, grow)) {
+          // The branch is warp-wide (tcgen05.ld / st are warp-collective) but the DECISION is per row: a row whose
+          // maximum did not outgrow its reference keeps it (alpha = 2^0 = 1 exactly), so a row's result depends only on
+          // its own scores — not on which rows share its warp, i.e. not on how the query rows are partitioned into
+          // tiles, ranks or launches (the sequence-parallel shards reproduce the single-GPU bits for any input).
+          const float m_next = grow ? m_new : m_ref;
           if (j > 0) {
             // PV_t(j-1) retired before s_full fired (same commit group), and PV_t(j)
             // is not issued until we arrive on p_full: O_t is ours to rescale.
-            const float alpha = ex2((m_ref - m_new) * p.scale_log2);
+            const float alpha = grow ? ex2((m_ref - m_next) * p.scale_log2) : 1.0f;
             l *= alpha;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -684,7 +689,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             tmem_st_wait();
           }
-          m_ref = m_new;
+          m_ref = m_next;
         }
         const float mb = m_ref * p.scale_log2;
         const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
