@@ -16,7 +16,8 @@ The head output is gathered at the end so every rank runs the identical schedule
 reference's xfuser USP path (videox_fun/dist/wan_xfuser.py:68-111, wan_transformer3d.py:802-816, :949-953,
 :1085-1086), which cannot run VideoCoF's chain-of-frames kwargs.
 
-* push exchange (opt-in, VCOF_SP_MODE=push; written at the end of round 1, NOT yet run on hardware): the head
+* push exchange (DEFAULT since round 2 when heads % P == 0: validated on hardware, bit-identical to one GPU at C2
+  widths, and the fastest of the three at P = 2 — profiles/r2_gpurun12_multi_gpu_n2.log): the head
   exchange without a collective call.  Every rank owns receive buffers in symmetric (NVLink peer-mapped) memory; the
   kernels that PRODUCE the exchanged tensors store straight into the other ranks' buffers — the norm/RoPE kernel for Q
   and K (vcof_rmsnorm_rope_scatter), a pack kernel for V, the attention kernel's own epilogue for the output on the way
@@ -88,6 +89,7 @@ class SequenceParallel:
         self.alloc_fn = symm_alloc    # injectable like attn_fn / copy_fn (CPU tests share plain tensors between threads)
         self._push = None
         self._push_key = None
+        self._push_ok = None          # result of the one-time symmetric-memory probe (use_push)
 
     def configure(self, kv_len, rows):
         """kv_len: number of real (non-padding) tokens of the full sequence; rows: tokens per rank."""
@@ -209,8 +211,38 @@ class SequenceParallel:
 
     # -- push exchange (producer kernels store into the peers' receive buffers) -----------------------
     def use_push(self, heads):
-        """VCOF_SP_MODE=push and heads divisible by P (otherwise the K/V all-gather serves)."""
-        return os.environ.get("VCOF_SP_MODE", "auto") == "push" and heads % self.world == 0
+        """Push exchange: default ("auto") whenever the heads divide by P and the ranks' buffers can be mapped into
+        each other (torch symmetric memory over NVLink peer access; probed once — a failed probe falls back to the
+        collective schemes with a note on stderr, it never raises).  Measured on 2 x B200, C2 step
+        (profiles/r2_gpurun12_multi_gpu_n2.log): push 2761 ms, K/V all-gather 2792 ms, head exchange 2820 ms.
+        VCOF_SP_MODE=heads|gather forces a collective scheme, =push insists (probe failures raise)."""
+        mode = os.environ.get("VCOF_SP_MODE", "auto")
+        if heads % self.world != 0 or mode in ("heads", "gather"):
+            return False
+        if mode == "push":
+            return True
+        return self._push_available()
+
+    def _push_available(self):
+        if self._push_ok is None:
+            ok = 1
+            dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+            try:
+                if dev.type != "cuda":
+                    raise RuntimeError("no CUDA device")
+                probe = torch.empty(8, dtype=torch.bfloat16, device=dev)
+                _t, peers, barrier = self.alloc_fn((8,), probe, self.group, "probe")
+                barrier()
+                ok = 1 if len(peers) == self.world else 0
+            except Exception as exc:                       # noqa: BLE001 — any failure means "use the collectives"
+                import sys
+                print(f"videocof_b200.dist: symmetric memory unavailable ({exc!r}); using NCCL exchanges", file=sys.stderr)
+                ok = 0
+            # every rank must take the same path: agree on the minimum
+            flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            self._push_ok = bool(int(flag.item()))
+        return self._push_ok
 
     def push_buffers(self, rows, C, like):
         key = (rows, C, like.dtype, str(like.device))
