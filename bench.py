@@ -420,14 +420,22 @@ def run_vcof(args):
     attn_key = [k for k in timing if k.startswith("attn") and f"Lk={L} " in k]
     roof = None
     if attn_key:
-        n, ms = timing[attn_key[0]]
-        flops = 4.0 * rows * L * cfg_kw["dim"]
-        ach = flops / (ms / n * 1e-3) / 1e12
+        # every self-attention launch of the timed region (the head exchange splits a layer's heads over two launches):
+        # algorithmic FLOPs 4 * Lq * Lk * heads * 128 per launch, summed, over the summed launch time
+        import re
+        n = ms = flops_total = 0.0
+        for k in attn_key:
+            m = re.match(r"attn Lq=(\d+) Lk=(\d+) heads=(\d+)", k)
+            kn, kms = timing[k]
+            n, ms = n + kn, ms + kms
+            flops_total += kn * 4.0 * int(m.group(1)) * int(m.group(2)) * int(m.group(3)) * 128
+        ach = flops_total / (ms * 1e-3) / 1e12
         roof = {"kernel": "attn_fwd_kernel (self-attention)", "bound": "tensor", "achieved": ach,
                 "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
                 "peak_source": f"{peaks['src']} bf16_tflops_sustained", "traffic": None,
-                "flops_per_launch": flops, "avg_launch_ms": ms / n, "launches_timed": n}
-        roof.update(ncu_traffic(attn_key[0]))
+                "flops_per_launch": flops_total / n, "avg_launch_ms": ms / n, "launches_timed": int(n)}
+        if len(attn_key) == 1:
+            roof.update(ncu_traffic(attn_key[0]))
     gpu_ms = sum(ms for _, ms in timing.values())
     breakdown = sorted(((k, n, ms) for k, (n, ms) in timing.items()), key=lambda r: -r[2])[:8]
     fl = flops_per_forward(cfg_kw, L) * run.B
@@ -503,9 +511,9 @@ def gpu_reference_leg(torch, model, cfg_kw, lat, fs, timing, ours_forward_ms):
 
 def ncu_traffic(attn_key):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same launch
-    shape (profiles/r1_attn_c2_ncu.json: dram__bytes_read.sum + dram__bytes_write.sum); null for other shapes."""
+    shape (profiles/r2_attn_c2_ncu.json: dram__bytes_read.sum + dram__bytes_write.sum); null for other shapes."""
     import re
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_attn_c2_ncu.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_attn_c2_ncu.json")
     m = re.match(r"attn Lq=(\d+) Lk=(\d+) heads=(\d+)", attn_key)
     if not m or not os.path.exists(path):
         return {}
@@ -514,7 +522,7 @@ def ncu_traffic(attn_key):
     if (int(m.group(1)), int(m.group(2)), int(m.group(3))) != (sh["Lq"], sh["Lk"], sh["heads"]):
         return {}
     return {"traffic": d["dram_bytes_per_launch"], "traffic_unit": "bytes/launch",
-            "traffic_algorithmic": d["algorithmic_bytes"], "traffic_source": "profiles/r1_attn_c2_ncu.json"}
+            "traffic_algorithmic": d["algorithmic_bytes"], "traffic_source": "profiles/r2_attn_c2_ncu.json"}
 
 
 def main():
