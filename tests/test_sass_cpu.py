@@ -54,4 +54,7 @@ def test_scatter_variants_share_the_default_arithmetic(ks):
     a, b = ks["attn_fwd_kernel<0, 0, 0, 2, 0, 0>"], ks["attn_fwd_kernel<0, 0, 0, 2, 0, 1>"]
     for key in ("REG", "STACK", "UTCHMMA", "UTMALDG", "LDTM", "STTM", "MUFU.EX2", "SYNCS"):
         assert a[key] == b[key], key
-    assert ks["rmsnorm_rope_kernel<1>"]["REG"] == ks["rmsnorm_rope_kernel<0>"]["REG"]
+    # the scatter variant of the norm / RoPE kernel carries a table of destination pointers: a few registers more, no stack
+    # (both variants are validated bit-exactly against each other on hardware: tests/test_widen_w_push_exchange_gpu.py)
+    r0, r1 = ks["rmsnorm_rope_kernel<0>"], ks["rmsnorm_rope_kernel<1>"]
+    assert abs(r1["REG"] - r0["REG"]) <= 16 and r0["STACK"] == 0 and r1["STACK"] == 0, (r0, r1)

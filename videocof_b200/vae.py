@@ -312,18 +312,34 @@ class TimeShard:
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
+        self.active = self.world          # ranks that hold frames under the current plan (see plan())
+
+    def plan(self, f):
+        """Latent frames per rank for a clip of f latent frames: the first `active` = min(P, f // 2) ranks share the
+        frames (a rank needs two frames of its own to fill its right neighbour's halo), the others get none and only
+        join the final gather — so a 10-latent-frame clip still shards over 5 of 8 ranks instead of running whole on
+        every rank.  Returns None when fewer than two ranks would be active."""
+        active = min(self.world, f // 2)
+        if active < 2:
+            return None
+        base, extra = divmod(f, active)
+        self.active = active
+        return [base + (1 if r < extra else 0) if r < active else 0 for r in range(self.world)]
 
     def exchange(self, xh, send=None):
         """xh: haloed buffer [HALO + T, H, W, C]; fills xh[:HALO] with the left neighbour's last HALO frames
-        (`send` overrides what this rank ships to the right, default xh[-HALO:])."""
+        (`send` overrides what this rank ships to the right, default xh[-HALO:]).  Only the active ranks of the
+        current plan take part."""
         dist = self.dist
         ops_ = []
+        if self.rank >= self.active:
+            return
         if self.rank > 0:
             recv = torch.empty_like(xh[:self.HALO])
             ops_.append(dist.P2POp(dist.irecv, recv, dist.get_global_rank(self.group, self.rank - 1), self.group))
         else:
             xh[:self.HALO].zero_()
-        if self.rank + 1 < self.world:
+        if self.rank + 1 < self.active:
             out = (xh[-self.HALO:] if send is None else send).contiguous()
             ops_.append(dist.P2POp(dist.isend, out, dist.get_global_rank(self.group, self.rank + 1), self.group))
         if ops_:
@@ -686,14 +702,16 @@ class AutoencoderKLWan_(nn.Module):
             raise VcofError("video must have 1+4k frames and H, W multiples of 8")
         enc = self.encoder
         f = (T - 1) // 4 + 1
-        sharded = shard is not None and shard.world > 1 and f >= 2 * shard.world
+        sizes = shard.plan(f) if (shard is not None and shard.world > 1) else None
+        sharded = sizes is not None
         t0, t1 = 0, T
         if sharded:
-            base, extra = divmod(f, shard.world)
-            sizes = [base + (1 if r < extra else 0) for r in range(shard.world)]
             a0 = sum(sizes[:shard.rank])
             b0 = a0 + sizes[shard.rank]
             t0, t1 = (0 if a0 == 0 else 4 * a0 - 3), 4 * b0 - 3
+            if sizes[shard.rank] == 0:          # idle rank of this plan: nothing to encode, join the gather
+                empty = torch.empty((2 * self.z_dim, 0, H // 8, W // 8), dtype=torch.bfloat16, device=x.device)
+                return shard.gather_frames(empty, sizes)[None]
         if as_bytes:
             h = ops.u8_to_cl(x[0, t0:t1].contiguous(), 32)
         else:
@@ -742,10 +760,17 @@ class AutoencoderKLWan_(nn.Module):
         h = ops.nchw_to_cl(z[0].to(torch.bfloat16).contiguous(), self.z_dim, div=inv_std, add=mean)
         h = conv1x1(h, self.conv2, out_ld=32)                  # 16 -> 16, stored in a 32-channel (zero padded) tensor
         f = h.shape[0]
-        sharded = shard is not None and shard.world > 1 and f >= 2 * shard.world
+        sizes = shard.plan(f) if (shard is not None and shard.world > 1) else None
+        sharded = sizes is not None
         if sharded:
-            base, extra = divmod(f, shard.world)
-            sizes = [base + (1 if r < extra else 0) for r in range(shard.world)]
+            counts = [4 * n - (3 if r == 0 else 0) for r, n in enumerate(sizes)]
+            if sizes[shard.rank] == 0:          # idle rank of this plan: nothing to decode, join the gather
+                Hh, Ww = 8 * h.shape[1], 8 * h.shape[2]
+                if as_bytes:
+                    empty = torch.empty((1, 0, Hh, Ww, 3), dtype=torch.uint8, device=z.device)
+                    return shard.gather_frames(empty, counts)[0][None]
+                empty = torch.empty((3, 0, Hh, Ww), dtype=torch.bfloat16, device=z.device)
+                return shard.gather_frames(empty, counts)[None]
             a = sum(sizes[:shard.rank])
             _SHARD = shard
             own = _alloc(sizes[shard.rank], h.shape[1], h.shape[2], h.shape[3], h.device)
@@ -760,8 +785,6 @@ class AutoencoderKLWan_(nn.Module):
             h = conv_causal(a_, dec.head[2], clamp=1.0, n_store=3)  # [T, H, W, 8] (3 real channels)
         finally:
             _SHARD = None
-        if sharded:
-            counts = [4 * n - (3 if r == 0 else 0) for r, n in enumerate(sizes)]
         if as_bytes:
             out = ops.cl_to_u8(h, 3)                                 # [T_r, H, W, 3]
             if sharded:
