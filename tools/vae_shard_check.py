@@ -31,6 +31,10 @@ def main():
     vae = vae.to(dev, torch.bfloat16).eval()
     res = {}
     cases = [("small", (1, 16, max(5, 2 * world + 1), 6, 10)), ("720p", (1, 16, max(6, 21 if world >= 4 else 6), 90, 160))]
+    if world >= 3:
+        # fewer than two latent frames per rank: only min(P, f // 2) ranks hold frames, the others idle and join the gather
+        cases.insert(1, ("idle_ranks", (1, 16, 5, 6, 10)))
+        cases.append(("720p_idle_ranks", (1, 16, world + 1, 90, 160)))
     for name, shape in cases:
         g = torch.Generator().manual_seed(1)
         z = torch.randn(*shape, generator=g).bfloat16().to(dev)
