@@ -658,7 +658,16 @@ extern "C" int vcof_gemm_bf16(const void* a, long long lda, const void* w, long 
   args.gate = gate;
   args.out = out;
   args.ldo = ldo;
-  args.group_m = 8;
+  {
+    // m-blocks per raster group (tiles of a group are walked m-fastest, so a wave of CTAs shares `group_m` A row blocks
+    // and ceil(waves / group_m) B column blocks).  VCOF_GEMM_GROUP_M overrides for A/B runs.
+    static const int group_m = [] {
+      const char* e = getenv("VCOF_GEMM_GROUP_M");
+      const int v = e ? atoi(e) : 0;
+      return v > 0 ? v : 16;      // measured (profiles/r2_gpurun18_gemm_group_sweep.log): 16 beats 8 by 1-7 %, 64 loses 10 %
+    }();
+    args.group_m = group_m;
+  }
   {
     static const int producers = [] {
       const char* e = getenv("VCOF_GEMM_PRODUCERS");
@@ -668,16 +677,19 @@ extern "C" int vcof_gemm_bf16(const void* a, long long lda, const void* w, long 
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // CTA-pair kernel (cta_group::2, 256 x 256 tiles).  Measured on B200 (profiles/r2_gpurun9_gemm_2cta_fixed.log):
-  // bias epilogue 75600 x 5120 x 5120: 1540 TFLOP/s against 1453 for the single-CTA kernel (cuBLAS: 1507); the GELU and
-  // gate + fp32-residual epilogues are 1-8 % SLOWER in pairs (two coupled epilogues per accumulator), so the default
-  // ("auto") uses pairs for the plain bias epilogue only.  VCOF_GEMM_2CTA=0: never, =1: all three epilogues.
+  // bias epilogue 75600 x 5120 x 5120: 1540 TFLOP/s against 1453 for the single-CTA kernel (cuBLAS: 1507).  Under ncu
+  // the pair kernel keeps the tensor pipe 99.6 % busy with every epilogue and needs 11 % fewer cycles than the single-CTA
+  // kernel — but a B200 under its power cap trades that for clock, so in milliseconds pairs win where their operand
+  // traffic is lowest: with raster groups of 16 m-blocks the bias and GELU epilogues gain 5-7 %
+  // (profiles/r2_gpurun18_gemm_group_sweep.log), the gate + fp32-residual epilogue (K = 13824: operands do not stay in
+  // L2) is level.  Default ("auto"): pairs for bias and bias+GELU.  VCOF_GEMM_2CTA=0: never, =1: all three epilogues.
   static const int pair_mode = [] {
     const char* e = getenv("VCOF_GEMM_2CTA");
     return e == nullptr ? 2 : (e[0] == '1' ? 1 : (e[0] == '0' ? 0 : 2));
   }();
   const bool pair_ok = !narrow && N >= 256 && M >= 256 &&
                        ((pair_mode == 1 && epilogue <= VCOF_EPI_BIAS_GATE_RES_F32) ||
-                        (pair_mode == 2 && epilogue == VCOF_EPI_BIAS_BF16));
+                        (pair_mode == 2 && (epilogue == VCOF_EPI_BIAS_BF16 || epilogue == VCOF_EPI_BIAS_GELU_BF16)));
   if (pair_ok) {
     // B box is this CTA's 128-row half of the 256-row tile
     rc = make_tmap_2d_bf16(&tmB, w, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, kBK, 128);
