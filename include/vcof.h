@@ -200,8 +200,16 @@ int vcof_nchw_to_cl(const void* x, void* y, int C, int Cp, long long thw, const 
 int vcof_cl_to_nchw(const void* x, long long ldx, void* y, int C, long long thw, const float* sub,
                     const float* mul, void* stream);
 
-/* p_bf16[rows, n] = softmax(s_f32[rows, n] * scale) — the d=384 single-head VAE attention runs as
- * GEMM (raw fp32 scores) -> this -> GEMM (wan_vae.py:244-266). */
+/* Fused single-head attention of the VAE's AttentionBlock (wan_vae.py:244-266: per frame,
+ * F.scaled_dot_product_attention over h*w tokens with d = C = 384).  qkv bf16 [T, N, >= 3C] with row pitch ld: the
+ * to_qkv output, q = columns [0, C), k = [C, 2C), v = [2C, 3C) (:251-256); out bf16 [T, N, C] with row pitch ldo:
+ * out[t] = softmax(q[t] k[t]^T * softmax_scale) v[t].  Scores and probabilities stay in tensor / shared memory.
+ * C must be 384. */
+int vcof_vae_attn(const void* qkv, long long ld, void* out, long long ldo, int T, int N, int C, float softmax_scale,
+                  void* stream);
+
+/* p_bf16[rows, n] = softmax(s_f32[rows, n] * scale) — the unfused form of the VAE attention (GEMM with raw fp32
+ * scores -> this -> GEMM), kept as the cross-check of vcof_vae_attn (VCOF_VAE_ATTN=unfused). */
 int vcof_softmax_rows(const float* s, long long lds, void* p, long long ldp, int rows, int n, float scale,
                       void* stream);
 

@@ -166,6 +166,12 @@ def vcof_softmax_rows(s, lds, p, ldp, rows, n, scale, stream):
     _mat(p, rows, n, ldp).copy_(emu.softmax_rows(_mat(s, rows, n, lds, torch.float32), scale))
 
 
+def vcof_vae_attn(qkv, ld, out, ldo, T, N, C, softmax_scale, stream):
+    x = _flat(qkv, (T * N - 1) * ld + 3 * C, torch.bfloat16).as_strided((T, N, 3 * C), (N * ld, ld, 1))
+    y = _flat(out, (T * N - 1) * ldo + C, torch.bfloat16).as_strided((T, N, C), (N * ldo, ldo, 1))
+    emu.vae_attn(x, C, softmax_scale, out=y)
+
+
 def vcof_rms_silu_cl(x, ldx, gamma, y, ldy, npos, C, silu, stream):
     emu.rms_silu_cl(_mat(x, npos, C, ldx), _flat(gamma, C, torch.float32), bool(silu), out=_mat(y, npos, C, ldy))
 
@@ -245,7 +251,7 @@ _EPI = {"bias": 0, "bias_gelu": 1, "bias_gate_res": 2, "bias_f32": 3, "raw_f32":
 STATEMENTS = {f.__name__: f for f in (vcof_attn_fwd, vcof_attn_fwd_scatter, vcof_rmsnorm_rope, vcof_rmsnorm_rope_blocked,
                                       vcof_rmsnorm_rope_scatter, vcof_copy_blocked, vcof_copy_scatter,
                                       vcof_copy_rows_scatter, vcof_cl_to_u8, vcof_u8_to_cl, vcof_gemm_bf16,
-                                      vcof_ln_modulate, vcof_patchify, vcof_unpatchify, vcof_linear_f32, vcof_softmax_rows,
+                                      vcof_ln_modulate, vcof_patchify, vcof_unpatchify, vcof_linear_f32, vcof_softmax_rows, vcof_vae_attn,
                                       vcof_rms_silu_cl, vcof_nchw_to_cl, vcof_cl_to_nchw, vcof_embed_rows, vcof_t5_rmsnorm,
                                       vcof_t5_attn, vcof_conv_igemm, vcof_conv_lines)}
 

@@ -184,6 +184,19 @@ def softmax_rows(s, scale, out=None):
     return torch.softmax(s.float() * scale, dim=-1).to(torch.bfloat16)
 
 
+def vae_attn(qkv, C, scale=None, out=None):
+    """Contract of vcof_vae_attn (include/vcof.h): per frame softmax(q k^T * scale) v with q | k | v the three C-column
+    groups of qkv [T, N, 3C]; fp32 accumulation, bf16 result."""
+    import math
+    scale = 1.0 / math.sqrt(C) if scale is None else scale
+    q, k, v = qkv[..., :C].float(), qkv[..., C:2 * C].float(), qkv[..., 2 * C:3 * C].float()
+    res = (torch.softmax(q @ k.transpose(1, 2) * scale, dim=-1) @ v).to(torch.bfloat16)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
 # ---- umT5 text encoder entry points (include/vcof.h: vcof_embed_rows, vcof_t5_rmsnorm, vcof_t5_attn) ----------------
 def embed_rows(ids, table, out=None):
     res = table[ids]
@@ -365,6 +378,6 @@ def install_t5(monkeypatch):
 def install(monkeypatch):
     from videocof_b200 import ops, vae
     for name in ("gemm", "conv_igemm", "conv_lines", "rms_silu_cl", "nchw_to_cl", "cl_to_nchw", "softmax_rows",
-                 "u8_to_cl", "cl_to_u8"):
+                 "vae_attn", "u8_to_cl", "cl_to_u8"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(vae.AutoencoderKLWan_, "_check", lambda self, x: None)

@@ -33,6 +33,7 @@ SIGNATURES = {
     "vcof_nchw_to_cl": [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p],
     "vcof_cl_to_nchw": [c_void_p, c_ll, c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p],
     "vcof_softmax_rows": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_float, c_void_p],
+    "vcof_vae_attn": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_float, c_void_p],
     "vcof_embed_rows": [c_void_p, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p],
     "vcof_t5_rmsnorm": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_ll, c_int, c_float, c_void_p],
     "vcof_t5_attn": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_void_p,

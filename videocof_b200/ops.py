@@ -469,6 +469,24 @@ def cl_to_u8(x, C, out=None):
     return out
 
 
+def vae_attn(qkv, C, scale=None, out=None):
+    """Fused single-head attention of the VAE AttentionBlock: qkv bf16 [T, N, 3C] (q | k | v along the last dim, the
+    to_qkv output) -> bf16 [T, N, C]; one launch for all T frames."""
+    _chk(qkv, torch.bfloat16, "vae_attn.qkv", 3)
+    T, N, C3 = qkv.shape
+    if C3 < 3 * C or qkv.stride(0) != N * qkv.stride(1):
+        raise _lib.VcofError(f"vae_attn: qkv {tuple(qkv.shape)} / strides {qkv.stride()} is not a dense stack of [N, 3C] frames")
+    if out is None:
+        out = torch.empty((T, N, C), dtype=torch.bfloat16, device=qkv.device)
+    _chk(out, torch.bfloat16, "vae_attn.out", 3)
+    if tuple(out.shape) != (T, N, C) or out.stride(0) != N * out.stride(1):
+        raise _lib.VcofError(f"vae_attn: out {tuple(out.shape)} / strides {out.stride()} does not match [T, N, C]")
+    scale = 1.0 / math.sqrt(C) if scale is None else scale
+    _call("vcof_vae_attn", qkv.data_ptr(), qkv.stride(1), out.data_ptr(), out.stride(1), T, N, C, float(scale), _stream(),
+          key=f"vae_attn T={T} N={N}")
+    return out
+
+
 def softmax_rows(s, scale, out=None):
     """bf16 softmax(s * scale) over the last dim of fp32 s [rows, n]."""
     _chk(s, torch.float32, "softmax.s", 2)

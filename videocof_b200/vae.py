@@ -521,6 +521,14 @@ def attn_block(x, blk):
     n = H * W
     y = rms_silu(x, blk.norm, silu=False)
     qkv = conv1x1(y, blk.to_qkv).reshape(T, n, 3 * C)
+    if C == 384 and os.environ.get("VCOF_VAE_ATTN", "fused") != "unfused":
+        # one fused tcgen05 launch for all frames: scores and probabilities never reach HBM (csrc/vae_attn_sm100.cu)
+        o = ops.vae_attn(qkv, C)
+        a = conv1x1(o.reshape(T, H, W, C), blk.proj)
+        out = _alloc(T, H, W, C, x.device)
+        torch.add(x, a, out=out)
+        return out
+    # unfused cross-check path (round 1): GEMM with raw fp32 scores -> row softmax -> GEMM, per frame
     o = torch.empty((T, n, C), dtype=torch.bfloat16, device=x.device)
     npad = (n + 7) // 8 * 8
     for t in range(T):
