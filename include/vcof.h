@@ -177,7 +177,7 @@ int vcof_conv_igemm(const void* x, const long long* x_dims, const long long* x_s
  *   kt, t0       temporal taps (1 | 3) and the input frame of the first one relative to the output frame
  *                (-(kt-1) for the causal convolution, plus the halo shift under temporal sharding)
  *   geom[7]      T_out, H_out, W_out, n_total, n_tile (channels per pass, <= 256), rows (output rows per work item,
- *                rows * roundup32(n_tile) <= 512), n_store
+ *                1..4 and <= min(5, 512 / roundup32(n_tile)), the accumulators of the kernel's TMEM ring), n_store
  * bias / residual / out / ldc / clamp / act_out / act_gamma as vcof_conv_igemm (plain output addressing).
  * Replaces CausalConv3d / Conv2d of wan_vae.py:21-40, 190-224 for the 3x3(x3) stride-1 layers. */
 int vcof_conv_lines(const void* x, const long long* x_dims, const long long* x_strides, const void* w, int cin, int kt,

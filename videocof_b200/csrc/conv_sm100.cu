@@ -456,12 +456,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 constexpr int kLnPix = 130;                          // 128 outputs + one halo pixel each side
 constexpr int kLnBytes = 17 * 512;                   // 130 x 64 B rounded up to the SW64 repeat (8704)
 constexpr int kLnMaxRows = 4;
+constexpr int kLnMaxAcc = 5;                         // accumulators in the TMEM ring (>= rows: the spare ones absorb the epilogue's burst)
 constexpr int kLnMaxRing = 8;
 
 struct LineArgs {
   ConvArgs c;          // geometry / epilogue fields (taps unused); c.n_tile = channels per N pass
   int kt, t0;          // temporal taps and the offset of the first one: t_in = t + t0 + dt
-  int rows;            // R: output rows per CTA work item (rows * n_tile <= 512)
+  int rows;            // R: output rows per CTA work item
+  int naccs;           // accumulators in the TMEM ring: min(kLnMaxAcc, 512 / roundup32(n_tile)) >= rows
   int ring;            // line ring depth
 };
 
@@ -476,9 +478,9 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t bar_wempty = bar_wfull + 16;                    // [2]
   const uint32_t bar_lfull = bar_wempty + 16;                    // [kLnMaxRing]
   const uint32_t bar_lempty = bar_lfull + 8 * kLnMaxRing;        // [kLnMaxRing]
-  const uint32_t bar_tfull = bar_lempty + 8 * kLnMaxRing;        // [kLnMaxRows]
-  const uint32_t bar_tempty = bar_tfull + 8 * kLnMaxRows;        // [kLnMaxRows]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * kLnMaxRing + 2 * kLnMaxRows);
+  const uint32_t bar_tfull = bar_lempty + 8 * kLnMaxRing;        // [kLnMaxAcc]
+  const uint32_t bar_tempty = bar_tfull + 8 * kLnMaxAcc;         // [kLnMaxAcc]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * kLnMaxRing + 2 * kLnMaxAcc);
   float* sBias = reinterpret_cast<float*>(smem + kCvData + 512);
   float* sGamma = sBias + kCvVecMax;
   for (int i = threadIdx.x; i < kCvVecMax; i += kCvThreads) {
@@ -494,7 +496,7 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wempty + 8 * i, 1); }
       for (int i = 0; i < kLnMaxRing; ++i) { mbar_init(bar_lfull + 8 * i, 1); mbar_init(bar_lempty + 8 * i, 1); }
-      for (int i = 0; i < kLnMaxRows; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+      for (int i = 0; i < kLnMaxAcc; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -507,6 +509,11 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   const int w_bytes = 9 * p.n_tile * 64;                         // nine [n_tile x 32 ch] tiles of one phase
   const int acc_stride = (p.n_tile + 31) & ~31;                  // TMEM columns per row accumulator
+  // Accumulator RING: row j of this CTA's i-th work item uses accumulator (i * R + j) % nacc.  With nacc > R the first
+  // rows of the next item land in accumulators that were drained long ago, so the MMA warp no longer waits while the
+  // epilogue works through the R rows that all complete within an item's last phase (measured: 27 % of the MMA warp's
+  // time with R = nacc = 4, profiles/r2_conv_lines_ncu_summary.txt).
+  const int nacc = a.naccs;
   const uint32_t smem_w = smem_u32(smem);                        // two weight buffers
   const uint32_t smem_l = smem_w + 2 * w_bytes;                  // then the line ring (w_bytes is a multiple of 512)
   const int wsegs = (p.W_out + 127) / 128, hgroups = (p.H_out + R - 1) / R;
@@ -579,9 +586,10 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (int r = 0; r < R + 2; ++r) {
             const uint64_t ldesc = ldesc0 + uint32_t(s) * (kLnBytes >> 4);
             mbar_wait(bar_lfull + 8 * s, lph);
-            if (phase == 0) {
-              // first MMA ever into accumulator j = r (through dh = 0): the epilogue of the previous item has drained it
-              if (r < R) mbar_wait(bar_tempty + 8 * r, (it & 1) ^ 1);
+            if (phase == 0 && r < R) {
+              // first MMA ever into row r's accumulator (through dh = 0): its previous user has been drained
+              const int g = it * R + r;
+              mbar_wait(bar_tempty + 8 * (g % nacc), ((g / nacc) & 1) ^ 1);
             }
             tc_fence_after();
             if (elect_one()) {
@@ -590,7 +598,8 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const int j = r - dh;                              // output row this line feeds through vertical tap dh
                 if (j < 0 || j >= R) continue;
                 const bool first = (phase == 0) && (dh == 0);      // first MMA ever into accumulator j of this item
-                const uint32_t d_tmem = tmem_base + j * acc_stride;
+                const int acc = (it * R + j) % nacc;
+                const uint32_t d_tmem = tmem_base + acc * acc_stride;
 #pragma unroll
                 for (int dw = 0; dw < 3; ++dw) {
                   // horizontal tap = the same line read dw pixels (64-byte rows) further in
@@ -599,7 +608,7 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                   umma_ss(d_tmem, ad, bd, idesc, !(first && dw == 0));
                   umma_ss(d_tmem, ad + 2, bd + 2, idesc, 1);
                 }
-                if (phase == phases - 1 && dh == 2) umma_commit(bar_tfull + 8 * j);   // row j is complete
+                if (phase == phases - 1 && dh == 2) umma_commit(bar_tfull + 8 * acc);   // row j is complete
               }
               umma_commit(bar_lempty + 8 * s);
               if (r == R + 1) umma_commit(bar_wempty + 8 * b);
@@ -619,16 +628,18 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int n_end = min(p.n_tile, p.n_total - n0);
       const int w = w0 + warp * 32 + lane;
       for (int j = 0; j < R; ++j) {
-        mbar_wait(bar_tfull + 8 * j, it & 1);
+        const int g = it * R + j;
+        const int acc = g % nacc;
+        mbar_wait(bar_tfull + 8 * acc, (g / nacc) & 1);
         tc_fence_after();
         bool released = false;
         if (h0 + j < p.H_out)
-          released = conv_epilogue_row(p, sBias, sGamma, tmem_base + ((warp * 32u) << 16) + j * acc_stride, t, h0 + j, w,
-                                       n0, n_end, bar_tempty + 8 * j);
+          released = conv_epilogue_row(p, sBias, sGamma, tmem_base + ((warp * 32u) << 16) + acc * acc_stride, t, h0 + j, w,
+                                       n0, n_end, bar_tempty + 8 * acc);
         if (!released) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * j);
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
       }
     }
@@ -869,7 +880,9 @@ extern "C" int vcof_conv_lines(const void* x, const long long* x_dims, const lon
                "vcof_conv_lines: fused norm needs gamma and a single channel pass");
   VCOF_REQUIRE(c.n_total <= kCvVecMax && c.n_total % 16 == 0 && c.n_tile % 16 == 0 && c.n_tile >= 16 && c.n_tile <= 256,
                "vcof_conv_lines: n_total %d / n_tile %d must be multiples of 16, n_tile <= 256", c.n_total, c.n_tile);
-  VCOF_REQUIRE(a.rows >= 1 && a.rows <= kLnMaxRows && a.rows * ((c.n_tile + 31) & ~31) <= 512,
+  a.naccs = 512 / ((c.n_tile + 31) & ~31);
+  if (a.naccs > kLnMaxAcc) a.naccs = kLnMaxAcc;
+  VCOF_REQUIRE(a.rows >= 1 && a.rows <= kLnMaxRows && a.rows <= a.naccs,
                "vcof_conv_lines: %d rows of %d channels do not fit 512 TMEM columns", a.rows, c.n_tile);
   VCOF_REQUIRE(ldc % 8 == 0, "vcof_conv_lines: ldc must be a multiple of 8");
   const int w_bytes = 9 * c.n_tile * 64;

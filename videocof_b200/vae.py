@@ -250,7 +250,11 @@ def _lines_plan(n_total):
         n_tile = 96
     else:
         n_tile = 64 if n_total % 64 == 0 else 16
-    rows = max(1, min(4, 512 // ((n_tile + 31) // 32 * 32)))
+    # the kernel keeps min(5, 512 // stride) accumulators in a TMEM ring; leaving `spare` of them beyond the rows of a
+    # work item lets the next item start while the epilogue still drains this one (VCOF_CONV_SPARE=0|1|2 for A/B runs)
+    nacc = min(5, 512 // ((n_tile + 31) // 32 * 32))
+    spare = int(os.environ.get("VCOF_CONV_SPARE", "1"))
+    rows = max(1, min(4, nacc - spare))
     return n_tile, rows
 
 
