@@ -239,9 +239,14 @@ def pack_conv_lines(conv):
     return _cached(conv, "lines", _ver(conv.weight, conv.bias), build)
 
 
-def _lines_plan(n_total):
-    """(n_tile, rows) of vcof_conv_lines: channels per pass and output rows per work item (rows accumulators of
-    roundup32(n_tile) TMEM columns each, 512 in total), favouring weight reuse over rows."""
+def _lines_plan(n_total, fused_act=False):
+    """(n_tile, rows) of vcof_conv_lines: channels per pass and output rows per work item, favouring weight reuse over
+    rows.  The kernel keeps nacc = min(5, 512 // roundup32(n_tile)) row accumulators in a TMEM ring.  Plain layers take
+    as many rows as fit (4: the weights of a phase serve more rows); layers with the fused RMS_norm + SiLU epilogue
+    (~2500 clk per row) leave two accumulators spare, so the next work item's first rows do not wait for the epilogue
+    to drain the burst of rows that complete in an item's last phase: 96 -> 96 + act at 720p 5.1 -> 4.5 ms, while plain
+    192- / 384-channel layers lose 1-8 % with fewer rows (profiles/r2_gpurun20_conv_ring_ab.log).
+    VCOF_CONV_SPARE=n forces n spare accumulators everywhere (A/B runs)."""
     if n_total <= 128:
         n_tile = n_total
     elif n_total % 128 == 0:
@@ -250,10 +255,9 @@ def _lines_plan(n_total):
         n_tile = 96
     else:
         n_tile = 64 if n_total % 64 == 0 else 16
-    # the kernel keeps min(5, 512 // stride) accumulators in a TMEM ring; leaving `spare` of them beyond the rows of a
-    # work item lets the next item start while the epilogue still drains this one (VCOF_CONV_SPARE=0|1|2 for A/B runs)
     nacc = min(5, 512 // ((n_tile + 31) // 32 * 32))
-    spare = int(os.environ.get("VCOF_CONV_SPARE", "1"))
+    spare = os.environ.get("VCOF_CONV_SPARE")
+    spare = int(spare) if spare is not None else (2 if fused_act else 0)
     rows = max(1, min(4, nacc - spare))
     return n_tile, rows
 
@@ -474,6 +478,8 @@ def _conv_causal_lines(x, conv, kt, residual, clamp, n_store, act_norm, want_raw
     dims, strides = _view5(xin)
     n_tile, rows = _lines_plan(n_total)
     fuse = act_norm is not None and n_tile == n_total
+    if fuse:
+        n_tile, rows = _lines_plan(n_total, fused_act=True)
     geom = [T, H, W, n_total, n_tile, rows, ns]
     t0 = -(kt - 1) + t_shift
     if fuse:
