@@ -4,7 +4,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libvcof.so")
+# VCOF_LIB: another build of libvcof.so (A/B timing of two kernel revisions inside one GPU call); default: the in-tree one
+LIB_PATH = os.environ.get("VCOF_LIB") or os.path.join(_HERE, "csrc", "libvcof.so")
 _lock = threading.Lock()
 _lib = None
 

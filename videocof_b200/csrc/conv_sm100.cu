@@ -577,28 +577,47 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint64_t wdesc0 = dflags | uint64_t((smem_w & 0x3FFFF) >> 4);
       const uint64_t ldesc0 = dflags | uint64_t((smem_l & 0x3FFFF) >> 4);
       const uint32_t w_tile = (p.n_tile * 64) >> 4;              // one (dh, dw) weight tile, in 16-byte units
-      int s = 0, b = 0, it = 0;
+      int s = 0, b = 0;
       uint32_t lph = 0, wph = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      int g0 = 0;               // (first row of this item) % nacc, advanced without divisions
+      uint32_t use_bits = 0;    // bit k = parity of accumulator k's next use
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int accs[kLnMaxRows];
+        uint32_t par = 0;       // bit j = parity of row j's use of its accumulator
+#pragma unroll
+        for (int j = 0; j < kLnMaxRows; ++j) {
+          int k = g0 + j;
+          if (k >= nacc) k -= nacc;
+          accs[j] = k;
+          if (j < R) {
+            par |= ((use_bits >> k) & 1u) << j;
+            use_bits ^= 1u << k;
+          }
+        }
+        g0 += R;
+        if (g0 >= nacc) g0 -= nacc;
         for (int phase = 0; phase < phases; ++phase) {
           const uint64_t wdesc = wdesc0 + uint32_t(b) * (uint32_t(w_bytes) >> 4);
           mbar_wait(bar_wfull + 8 * b, wph);
-          for (int r = 0; r < R + 2; ++r) {
+          // unrolled over the (at most six) lines of a phase: the row a line feeds through tap dh and that row's
+          // accumulator are then compile-time register picks instead of per-line select chains in the issuing warp
+#pragma unroll
+          for (int r = 0; r < kLnMaxRows + 2; ++r) {
+            if (r >= R + 2) break;
             const uint64_t ldesc = ldesc0 + uint32_t(s) * (kLnBytes >> 4);
             mbar_wait(bar_lfull + 8 * s, lph);
             if (phase == 0 && r < R) {
               // first MMA ever into row r's accumulator (through dh = 0): its previous user has been drained
-              const int g = it * R + r;
-              mbar_wait(bar_tempty + 8 * (g % nacc), ((g / nacc) & 1) ^ 1);
+              mbar_wait(bar_tempty + 8 * accs[r < kLnMaxRows ? r : 0], ((par >> r) & 1u) ^ 1u);
             }
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
               for (int dh = 0; dh < 3; ++dh) {
                 const int j = r - dh;                              // output row this line feeds through vertical tap dh
-                if (j < 0 || j >= R) continue;
+                if (j < 0 || j >= kLnMaxRows || j >= R) continue;
                 const bool first = (phase == 0) && (dh == 0);      // first MMA ever into accumulator j of this item
-                const int acc = (it * R + j) % nacc;
+                const int acc = accs[j];
                 const uint32_t d_tmem = tmem_base + acc * acc_stride;
 #pragma unroll
                 for (int dw = 0; dw < 3; ++dw) {
@@ -621,16 +640,19 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
   } else if (warp < 4) {        // ---- epilogue: rows drain one by one as they complete ----
-    int it = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+    int g0 = 0;
+    uint32_t use_bits = 0;      // same ring bookkeeping as the MMA warp
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int t, h0, w0, n0;
       decode(item, t, h0, w0, n0);
       const int n_end = min(p.n_tile, p.n_total - n0);
       const int w = w0 + warp * 32 + lane;
       for (int j = 0; j < R; ++j) {
-        const int g = it * R + j;
-        const int acc = g % nacc;
-        mbar_wait(bar_tfull + 8 * acc, (g / nacc) & 1);
+        int acc = g0 + j;
+        if (acc >= nacc) acc -= nacc;
+        const uint32_t parity = (use_bits >> acc) & 1u;
+        use_bits ^= 1u << acc;
+        mbar_wait(bar_tfull + 8 * acc, parity);
         tc_fence_after();
         bool released = false;
         if (h0 + j < p.H_out)
@@ -642,6 +664,8 @@ conv_lines_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
       }
+      g0 += R;
+      if (g0 >= nacc) g0 -= nacc;
     }
   }
 
