@@ -682,14 +682,16 @@ extern "C" int vcof_gemm_bf16(const void* a, long long lda, const void* w, long 
   // kernel — but a B200 under its power cap trades that for clock, so in milliseconds pairs win where their operand
   // traffic is lowest: with raster groups of 16 m-blocks the bias and GELU epilogues gain 5-7 %
   // (profiles/r2_gpurun18_gemm_group_sweep.log), the gate + fp32-residual epilogue (K = 13824: operands do not stay in
-  // L2) is level.  Default ("auto"): pairs for bias and bias+GELU.  VCOF_GEMM_2CTA=0: never, =1: all three epilogues.
+  // L2) is level, at K = 5120 it gains 7 % (1396 vs 1305 TFLOP/s, gpurun call 21).  Default ("auto"): pairs for bias,
+  // bias+GELU, and gate + residual up to K = 8192.  VCOF_GEMM_2CTA=0: never, =1: all three epilogues.
   static const int pair_mode = [] {
     const char* e = getenv("VCOF_GEMM_2CTA");
     return e == nullptr ? 2 : (e[0] == '1' ? 1 : (e[0] == '0' ? 0 : 2));
   }();
   const bool pair_ok = !narrow && N >= 256 && M >= 256 &&
                        ((pair_mode == 1 && epilogue <= VCOF_EPI_BIAS_GATE_RES_F32) ||
-                        (pair_mode == 2 && (epilogue == VCOF_EPI_BIAS_BF16 || epilogue == VCOF_EPI_BIAS_GELU_BF16)));
+                        (pair_mode == 2 && (epilogue == VCOF_EPI_BIAS_BF16 || epilogue == VCOF_EPI_BIAS_GELU_BF16 ||
+                                            (epilogue == VCOF_EPI_BIAS_GATE_RES_F32 && K <= 8192))));
   if (pair_ok) {
     // B box is this CTA's 128-row half of the 256-row tile
     rc = make_tmap_2d_bf16(&tmB, w, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, kBK, 128);
