@@ -81,6 +81,10 @@ def _apply(weight, up, down, scale, device):
         ops.gemm(a, b, None, "gate_accum", out=w, gate=gate)
     if w is not weight:
         weight.copy_(w)
+    else:
+        # the kernel wrote through the raw pointer: bump the tensor's version counter so that anything cached on
+        # `weight._version` (the small fp32 vector caches of dit.py / vae.py, packed conv weights) is rebuilt
+        weight.mul_(1)          # x * 1 keeps every bit (x + 0 would turn -0.0 into +0.0)
 
 
 def _run(pipeline, state_dict, multiplier, device, dtype, transformer_only, sub_transformer_name, sign):

@@ -18,5 +18,6 @@ if REFERENCE_ROOT is not None:
             for _n in dir(_ref):
                 if not _n.startswith("_") and _n not in ("merge_lora", "unmerge_lora"):
                     globals()[_n] = getattr(_ref, _n)
-        except ImportError:            # the reference module needs diffusers; the merge entry points do not
-            pass
+        except Exception as _exc:      # noqa: BLE001 — the reference module's own imports (diffusers, cv2 …) may be
+            import warnings            # missing or of another version; what the overlay itself exports needs none of it
+            warnings.warn(f"videox_fun overlay: optional re-export of {_path} skipped ({_exc!r})")
