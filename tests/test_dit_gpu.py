@@ -160,3 +160,44 @@ def test_batched_cfg_forward_is_bit_identical_to_the_per_sample_loop(monkeypatch
         monkeypatch.setenv("VCOF_DIT_BATCHED", "1")
         batched = model(**args)
     assert torch.equal(loop, batched)
+
+
+def test_context_cache_forward_is_bit_identical(monkeypatch):
+    """SURVEY §8a a4 / a11 (K3 / K10): the text embedding and the cross-attention K / V of it are step-invariant;
+    with `enable_context_cache` they are computed at the first forward only, and two consecutive cached forwards
+    (different latents and timesteps, same prompt embeddings) equal the uncached ones bit for bit — per-sample loop
+    and batched CFG path — with fewer launches on the second."""
+    from videocof_b200 import ops
+    ckw, shape, n_ctx, B = DIT_CASES["dit_tiny_b2"]
+    cfg = DiTConfig(**ckw)
+    params = make_dit_params(cfg, seed=11)
+    x, ctx, t = dit_inputs(shape, n_ctx, cfg.text_dim, B, seed=23)
+    f = shape[1]
+    seq_len = f * (shape[2] // 2) * (shape[3] // 2)
+    model = build_cuda_model(cfg, params)
+    ctx = [c.cuda().bfloat16() for c in ctx]
+    kw = dict(context=ctx, seq_len=seq_len, **ROPE_MODES["cot"](f, B))
+    steps = [(x.cuda().bfloat16(), t.cuda()), ((x * 0.5).cuda().bfloat16(), (t * 0.5).cuda())]
+    for batched in ("1", "0"):
+        monkeypatch.setenv("VCOF_DIT_BATCHED", batched)
+        with torch.no_grad():
+            model.disable_context_cache()
+            ref, n_ref = [], []
+            for xx, tt in steps:
+                ops.reset_launches()
+                ref.append(model(x=xx, t=tt, **kw))
+                n_ref.append(ops.launches())
+            model.enable_context_cache()
+            got, n_got = [], []
+            for xx, tt in steps:
+                ops.reset_launches()
+                got.append(model(x=xx, t=tt, **kw))
+                n_got.append(ops.launches())
+            model.disable_context_cache()
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+        layers = len(model.blocks)
+        assert n_ref[0] == n_ref[1]
+        # second cached forward: no text embedding (2 GEMMs per sample) and no K / norm / V launches in any block
+        saved = B * 2 + 3 * layers * (1 if batched == "1" else B)
+        assert n_got[1] == n_ref[1] - saved, (n_got, n_ref, saved)

@@ -301,3 +301,64 @@ def test_batched_forward_is_bit_identical_to_the_per_sample_loop(monkeypatch, pa
         monkeypatch.setenv("VCOF_DIT_BATCHED", "1")
         batched = model(**args)
     assert torch.equal(loop, batched)
+
+
+def test_context_cache_is_bit_identical_and_invalidates(monkeypatch):
+    """SURVEY §8a a4 / a11 (K3 / K10): with `enable_context_cache` the text embedding and the blocks' cross-attention
+    K / V are computed once per prompt embedding; a cached forward equals an uncached one bit for bit (per-sample loop
+    and batched CFG path), and an in-place edit of the embedding or of a weight they were computed from misses."""
+    vcof_emulator.install_dit(monkeypatch)
+    cfg, params, x, ctx, t, f, seq_len, B, shape = case("dit_tiny_b2")
+    model = build_model(cfg, params)
+    ctx = [c.bfloat16() for c in ctx]
+    kw = ROPE_MODES["cot"](f, B)
+
+    def fwd(xx, tt):
+        with torch.no_grad():
+            return model(x=xx.bfloat16(), t=tt, context=ctx, seq_len=seq_len, **kw)
+
+    calls = {"n": 0}
+    orig = type(model.blocks[0]).context_kv
+
+    def counting(self, c):
+        calls["n"] += 1
+        return orig(self, c)
+
+    monkeypatch.setattr(type(model.blocks[0]), "context_kv", counting)
+    layers = len(model.blocks)
+    for batched in ("1", "0"):
+        monkeypatch.setenv("VCOF_DIT_BATCHED", batched)
+        model.disable_context_cache()
+        calls["n"] = 0
+        ref = [fwd(x, t), fwd(x * 0.5, t * 0.5)]
+        uncached_calls = calls["n"]
+        assert uncached_calls == (2 * layers if batched == "1" else 2 * B * layers)
+        model.enable_context_cache()
+        calls["n"] = 0
+        got = [fwd(x, t), fwd(x * 0.5, t * 0.5)]
+        assert calls["n"] == B * layers                      # first forward only, once per distinct embedding
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+        # an in-place edit of one embedding recomputes that embedding alone, and the result follows it
+        ctx[0].mul_(0.5)
+        y = fwd(x, t)
+        assert calls["n"] == (B + 1) * layers
+        model.disable_context_cache()
+        assert torch.equal(y, fwd(x, t)) and not torch.equal(y, ref[0])
+        # an in-place edit of a weight the cache depends on misses for every embedding
+        model.enable_context_cache()
+        fwd(x, t)
+        calls["n"] = 0
+        model.blocks[1].cross_attn.v.weight.detach().mul_(1.25)
+        y = fwd(x, t)
+        assert calls["n"] == B * layers
+        model.disable_context_cache()
+        assert torch.equal(y, fwd(x, t))
+        ctx[0].mul_(2.0)
+        model.blocks[1].cross_attn.v.weight.detach().mul_(0.8)
+    # the cache is bounded
+    model.enable_context_cache(max_entries=2)
+    for s in (1.0, 0.9, 0.8):
+        with torch.no_grad():
+            model(x=x.bfloat16(), t=t, context=[c * s for c in ctx], seq_len=seq_len, **kw)
+    assert len(model._ctx_cache["entries"]) == 2

@@ -1,6 +1,7 @@
 """Host-side plumbing of videocof_b200.pipeline.WanPipeline on CPU with stub DiT / VAE modules: chain-of-frames
 latent assembly, frame-split kwargs, CFG batching, frozen source frames, split ground/edit decode
 (reference videox_fun/pipeline/pipeline_wan.py:381-428, 592-799)."""
+import pytest
 import torch
 
 from videocof_b200.pipeline import WanPipeline, randn_tensor
@@ -110,3 +111,49 @@ def test_randn_tensor_cpu_generator_is_device_independent():
     a = randn_tensor((2, 3), generator=torch.Generator().manual_seed(3), device="cpu", dtype=torch.float32)
     b = torch.randn((2, 3), generator=torch.Generator().manual_seed(3))
     assert torch.equal(a, b)
+
+
+def test_context_cache_is_scoped_to_the_denoising_loop(monkeypatch):
+    """`__call__` turns the DiT's step-invariant context cache on for its loop and frees it afterwards — also when a
+    step raises — leaves a cache the caller enabled alone, and VCOF_CONTEXT_CACHE=0 keeps it off."""
+    class CachingDiT(StubDiT):
+        def __init__(self, fail_at=None):
+            super().__init__()
+            self._ctx_cache, self.seen, self.events, self.fail_at = None, [], [], fail_at
+
+        def enable_context_cache(self, max_entries=4):
+            self.events.append("on")
+            self._ctx_cache = {"max": max_entries, "entries": []}
+
+        def disable_context_cache(self):
+            self.events.append("off")
+            self._ctx_cache = None
+
+        def __call__(self, x, **kw):
+            self.seen.append(self._ctx_cache is not None)
+            if self.fail_at == len(self.seen):
+                raise RuntimeError("step failed")
+            return super().__call__(x, **kw)
+
+    def run(dit):
+        pipe = WanPipeline(None, None, StubVAE(), dit, FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1))
+        return pipe(video=torch.zeros(1, 3, 5, 16, 16), prompt_embeds=[torch.randn(2, 8)], height=16, width=16,
+                    source_frames=5, reasoning_frames=4, num_inference_steps=4, guidance_scale=1.0, shift=3, cot=True,
+                    generator=torch.Generator().manual_seed(1))
+
+    dit = CachingDiT()
+    run(dit)
+    assert dit.seen == [True] * 4 and dit.events == ["on", "off"] and dit._ctx_cache is None
+    dit = CachingDiT(fail_at=2)
+    with pytest.raises(RuntimeError, match="step failed"):
+        run(dit)
+    assert dit.events == ["on", "off"] and dit._ctx_cache is None
+    dit = CachingDiT()
+    dit.enable_context_cache()
+    run(dit)
+    assert dit.events == ["on"] and dit._ctx_cache is not None          # the caller's cache is the caller's to free
+    monkeypatch.setenv("VCOF_CONTEXT_CACHE", "0")
+    dit = CachingDiT()
+    run(dit)
+    assert dit.seen == [False] * 4 and dit.events == []
+    run(StubDiT())                                                       # a DiT without the cache surface: untouched

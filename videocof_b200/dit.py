@@ -113,9 +113,18 @@ class WanAttentionBlock(nn.Module):
         self.modulation = nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5)
 
     # -- fused single-sample path -------------------------------------------------------------
-    def run(self, x, e, ctx, rope, kv_len, ws, sp=None):
+    def context_kv(self, ctx):
+        """Cross-attention keys and values of the embedded text, ctx bf16 [S,C] (:310-336: k = norm_k(k(context)),
+        v = v(context)).  They depend on the prompt and the weights only, not on the timestep or the latents."""
+        ca = self.cross_attn
+        kc = ops.gemm(ctx, ca.k.weight, ca.k.bias, "bias")
+        ops.rmsnorm_rope_(kc, ca.norm_k.weight, ca.eps, self.dim // self.num_heads, None)
+        return kc, ops.gemm(ctx, ca.v.weight, ca.v.bias, "bias")
+
+    def run(self, x, e, ctx, rope, kv_len, ws, sp=None, ckv=None):
         """x fp32 [L,C] (updated in place and returned); e fp32 [6,C] = modulation + e0;
-        ctx bf16 [S,C]; rope: ops.RopeSpec; sp: optional sequence-parallel context (dist.py)."""
+        ctx bf16 [S,C]; rope: ops.RopeSpec; sp: optional sequence-parallel context (dist.py);
+        ckv: this block's (K, V) of ctx when the model's context cache holds them (else computed here)."""
         sa, ca = self.self_attn, self.cross_attn
         n, hd = self.num_heads, self.dim // self.num_heads
         # self-attention (:495-499)
@@ -169,9 +178,7 @@ class WanAttentionBlock(nn.Module):
             raise NotImplementedError("cross_attn_norm=False is not on the VideoCoF path")
         ops.gemm(ws.a, ca.q.weight, ca.q.bias, "bias", out=ws.q)
         ops.rmsnorm_rope_(ws.q, ca.norm_q.weight, ca.eps, hd, None)
-        kc = ops.gemm(ctx, ca.k.weight, ca.k.bias, "bias")
-        ops.rmsnorm_rope_(kc, ca.norm_k.weight, ca.eps, hd, None)
-        vc = ops.gemm(ctx, ca.v.weight, ca.v.bias, "bias")
+        kc, vc = ckv if ckv is not None else self.context_kv(ctx)
         ops.attention(ws.q, kc, vc, n, out=ws.a)
         ops.gemm(ws.a, ca.o.weight, ca.o.bias, "bias_gate_res", out=x, gate=None)
         # MLP (:507-511)
@@ -180,7 +187,7 @@ class WanAttentionBlock(nn.Module):
         ops.gemm(ws.h, self.ffn[2].weight, self.ffn[2].bias, "bias_gate_res", out=x, gate=e[5])
         return x
 
-    def run_batched(self, X, es, ctx, ropes, kv_lens, ws, rows):
+    def run_batched(self, X, es, ctx, ropes, kv_lens, ws, rows, ckv=None):
         """Batch-aware block (classifier-free guidance: the uncond + cond samples of one step, pipeline_wan.py:700).
         X fp32 [B*rows, C]: the samples' residual streams stacked along M (updated in place); es[b] fp32 [6, C];
         ctx bf16 [B*S, C] the samples' text contexts stacked; ropes / kv_lens per sample.
@@ -189,11 +196,11 @@ class WanAttentionBlock(nn.Module):
         cross-attention q / k / v / o and the first FFN Linear: the weights stream once per step instead of once per
         sample — while what depends on the sample runs per row range: AdaLN modulation, RoPE (positions restart),
         attention (keys of one sample), and the two gated residual GEMMs (per-sample gate vector).  Row-wise the
-        arithmetic is that of `run`, so the result is bit-identical to the per-sample loop."""
+        arithmetic is that of `run`, so the result is bit-identical to the per-sample loop.
+        ckv: per sample, this block's cached (K, V) of that sample's context (see `run`)."""
         sa, ca = self.self_attn, self.cross_attn
         n, hd = self.num_heads, self.dim // self.num_heads
         B = len(es)
-        S = ctx.shape[0] // B
         rng = [slice(b * rows, (b + 1) * rows) for b in range(B)]
         for b in range(B):
             ops.ln_modulate(X[rng[b]], None, None, es[b][0], es[b][1], self.eps, out=ws.a[rng[b]])
@@ -212,12 +219,12 @@ class WanAttentionBlock(nn.Module):
                         None, None, self.eps, out=ws.a)
         ops.gemm(ws.a, ca.q.weight, ca.q.bias, "bias", out=ws.q)
         ops.rmsnorm_rope_(ws.q, ca.norm_q.weight, ca.eps, hd, None)
-        kc = ops.gemm(ctx, ca.k.weight, ca.k.bias, "bias")
-        ops.rmsnorm_rope_(kc, ca.norm_k.weight, ca.eps, hd, None)
-        vc = ops.gemm(ctx, ca.v.weight, ca.v.bias, "bias")
+        if ckv is None:
+            S = ctx.shape[0] // B
+            kc, vc = self.context_kv(ctx)
+            ckv = [(kc[b * S:(b + 1) * S], vc[b * S:(b + 1) * S]) for b in range(B)]
         for b in range(B):
-            cs = slice(b * S, (b + 1) * S)
-            ops.attention(ws.q[rng[b]], kc[cs], vc[cs], n, out=ws.a[rng[b]])
+            ops.attention(ws.q[rng[b]], ckv[b][0], ckv[b][1], n, out=ws.a[rng[b]])
         ops.gemm(ws.a, ca.o.weight, ca.o.bias, "bias_gate_res", out=X, gate=None)
         for b in range(B):
             ops.ln_modulate(X[rng[b]], None, None, es[b][3], es[b][4], self.eps, out=ws.a[rng[b]])
@@ -424,6 +431,7 @@ class WanTransformer3DModel(nn.Module):
         self.sp_world_rank = 0
         self._sp = None
         self._ws = _Workspace()
+        self._ctx_cache = None
         self.init_weights()
 
     # ---- diffusers-ModelMixin surface the callers touch -----------------------------------------
@@ -475,6 +483,49 @@ class WanTransformer3DModel(nn.Module):
 
     def disable_cfg_skip(self):
         self.cfg_skip_ratio, self.current_steps, self.num_inference_steps = None, 0, None
+
+    # ---- step-invariant context work ("K3 / K10") ---------------------------------
+    def enable_context_cache(self, max_entries=4):
+        """Keep, per distinct prompt embedding, the embedded text (:936-942) and every block's cross-attention K / V
+        of it (:310-336) across forwards: they depend on the prompt and the weights only, and the reference recomputes
+        all 2 + 3 x layers launches at every timestep.  Opt-in and scoped: `WanPipeline.__call__` turns it on around
+        its denoising loop — where the embeddings are fixed before the first step (pipeline_wan.py:606) — and off
+        (freed) after it; a bare `forward` recomputes, like the reference.  The kernels and their inputs are the same
+        ones, so a cached forward is bit-identical to an uncached one.
+
+        An entry is keyed by the embedding tensor's storage address, shape and version counter and HOLDS the tensor (an
+        address cannot be recycled while its entry lives), plus the address / version of every weight it was computed
+        from: in-place edits (LoRA merge / unmerge, load_state_dict) and moved weights miss."""
+        self._ctx_cache = {"max": int(max_entries), "entries": []}
+
+    def disable_context_cache(self):
+        self._ctx_cache = None
+
+    def _context_weights_key(self):
+        ps = [p for p in self.text_embedding.parameters()]
+        for blk in self.blocks:
+            ca = blk.cross_attn
+            ps += [ca.k.weight, ca.k.bias, ca.v.weight, ca.v.bias, ca.norm_k.weight]
+        return tuple((p.data_ptr(), p._version) for p in ps)
+
+    def _contexts(self, context, n):
+        """Per sample: (embedded text bf16 [text_len, C], per-block (K, V) list or None when the cache is off)."""
+        cache = getattr(self, "_ctx_cache", None)
+        if cache is None:
+            return [(self._text_embed(context[b]), None) for b in range(n)]
+        wkey = self._context_weights_key()
+        out = []
+        for b in range(n):
+            c = context[b]
+            key = (c.data_ptr(), c._version, tuple(c.shape), tuple(c.stride()), c.dtype, str(c.device), wkey)
+            hit = next((e for e in cache["entries"] if e[0] == key), None)
+            if hit is None:
+                ctx = self._text_embed(c)
+                hit = (key, c, ctx, [blk.context_kv(ctx) for blk in self.blocks])
+                cache["entries"].append(hit)
+                del cache["entries"][:-cache["max"]]
+            out.append((hit[2], hit[3]))
+        return out
 
     def enable_riflex(self, k=6, L_test=66, L_test_scale=4.886):
         d = self.d
@@ -571,6 +622,7 @@ class WanTransformer3DModel(nn.Module):
         outs = []
         tc = self.teacache
         embeds = [self._time_embed(t[b]) for b in range(len(xs))]
+        ctxs = self._contexts(context, len(xs))
 
         # TeaCache gate (:956-1031): ONE decision per forward, from the modulated timestep embedding of the batch
         should_calc = True
@@ -598,7 +650,7 @@ class WanTransformer3DModel(nn.Module):
         shapes = {tuple(u.shape) for u in xs}
         if (len(xs) >= 2 and P == 1 and len(shapes) == 1 and os.environ.get("VCOF_DIT_BATCHED", "1") != "0"
                 and not (tc is not None and not should_calc)):
-            return self._forward_batched(xs, t, context, seq_len, cond_flag, frame_split_indices,
+            return self._forward_batched(xs, t, ctxs, seq_len, cond_flag, frame_split_indices,
                                          ground_frame_indices, embeds, tc)
 
         for b, u in enumerate(xs):
@@ -614,7 +666,7 @@ class WanTransformer3DModel(nn.Module):
             ops.gemm(a, self.patch_embedding.weight.view(C, -1), self.patch_embedding.bias, "bias_f32",
                      out=xb[:L])
             e, e0 = embeds[b]
-            ctx = self._text_embed(context[b])
+            ctx, ckv = ctxs[b]
             fs = frame_split_indices[b] if frame_split_indices is not None and b < len(frame_split_indices) else None
             gr = ground_frame_indices[b] if (fs is not None and ground_frame_indices is not None
                                              and b < len(ground_frame_indices)) else None
@@ -634,7 +686,8 @@ class WanTransformer3DModel(nn.Module):
                 ori = xb.clone() if tc is not None else None
                 ws = self._ws.get(dev, rows, C, self.ffn_dim)
                 for i, blk in enumerate(self.blocks):
-                    blk.run(xb, mod_all[i], ctx, rope, L, ws, sp if P > 1 else None)
+                    blk.run(xb, mod_all[i], ctx, rope, L, ws, sp if P > 1 else None,
+                            ckv[i] if ckv is not None else None)
                 if tc is not None:
                     res = xb - ori
                     residuals.append(res.cpu() if tc.offload else res)
@@ -658,8 +711,9 @@ class WanTransformer3DModel(nn.Module):
                 tc.reset()
         return torch.stack(outs)
 
-    def _forward_batched(self, xs, t, context, seq_len, cond_flag, frame_split_indices, ground_frame_indices, embeds, tc):
-        """`_forward` for B >= 2 same-shape samples on one GPU: tokens stacked [B*seq_len, C] (see run_batched)."""
+    def _forward_batched(self, xs, t, ctxs, seq_len, cond_flag, frame_split_indices, ground_frame_indices, embeds, tc):
+        """`_forward` for B >= 2 same-shape samples on one GPU: tokens stacked [B*seq_len, C] (see run_batched).
+        ctxs: `_contexts` of the batch."""
         dev = xs[0].device
         C, B = self.dim, len(xs)
         cin, F_, H_, W_ = xs[0].shape
@@ -668,22 +722,23 @@ class WanTransformer3DModel(nn.Module):
         assert L <= seq_len, "seq_len shorter than the token count"          # (:906)
         X = torch.zeros((B * seq_len, C), dtype=torch.float32, device=dev) if seq_len > L else \
             torch.empty((B * seq_len, C), dtype=torch.float32, device=dev)
-        ctxs, ropes, mods = [], [], []
+        ropes, mods = [], []
         for b, u in enumerate(xs):
             a = ops.patchify(u.to(torch.bfloat16).contiguous())
             ops.gemm(a, self.patch_embedding.weight.view(C, -1), self.patch_embedding.bias, "bias_f32",
                      out=X[b * seq_len:b * seq_len + L])
-            ctxs.append(self._text_embed(context[b]))
             fs = frame_split_indices[b] if frame_split_indices is not None and b < len(frame_split_indices) else None
             gr = ground_frame_indices[b] if (fs is not None and ground_frame_indices is not None
                                              and b < len(ground_frame_indices)) else None
             ropes.append(make_rope_spec(self.freqs, dev, f, h, w, fs, gr))
             mods.append(self._mod_stack() + embeds[b][1])                    # [layers, 6, C] (:491)
-        ctx = torch.cat(ctxs, dim=0)
+        cached = ctxs[0][1] is not None
+        ctx = None if cached else torch.cat([c for c, _ in ctxs], dim=0)
         ori = X.clone() if tc is not None else None
         ws = self._ws.get(dev, B * seq_len, C, self.ffn_dim)
         for i, blk in enumerate(self.blocks):
-            blk.run_batched(X, [m[i] for m in mods], ctx, ropes, [L] * B, ws, seq_len)
+            blk.run_batched(X, [m[i] for m in mods], ctx, ropes, [L] * B, ws, seq_len,
+                            [kv[i] for _, kv in ctxs] if cached else None)
         if tc is not None:
             res = (X - ori).view(B, seq_len, C)
             res = res.cpu() if tc.offload else res

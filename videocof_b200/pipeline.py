@@ -7,6 +7,7 @@ The two heavy callees are the libvcof-backed models (videocof_b200.dit / videoco
 everything in this file is host-side plumbing on small tensors.
 """
 import math
+import os
 from dataclasses import dataclass
 from typing import Any, Optional
 
@@ -253,33 +254,45 @@ class WanPipeline:
         ps = self.transformer.config.patch_size
         seq_len = math.ceil((h_lat * w_lat) / (ps[1] * ps[2]) * f_lat)
         self.transformer.num_inference_steps = num_inference_steps
-        for i, t in enumerate(timesteps):
-            self.transformer.current_steps = i
-            if self._interrupt:
-                continue
-            x = torch.cat([latents] * 2) if do_cfg else latents
-            if hasattr(self.scheduler, "scale_model_input"):
-                x = self.scheduler.scale_model_input(x, t)
-            timestep = t.expand(x.shape[0])
-            fsi = gfi = None
-            if repeat_rope and video is not None:
-                fsi = [condition_count] * x.shape[0]
-                if cot:
-                    gfi = [(condition_count, condition_count + ground_latent_count)] * x.shape[0]
-            noise_pred = self.transformer(x=x, context=in_prompt_embeds, t=timestep, seq_len=seq_len,
-                                          frame_split_indices=fsi, ground_frame_indices=gfi)
-            if do_cfg:
-                uncond, text = noise_pred.chunk(2)
-                noise_pred = uncond + self.guidance_scale * (text - uncond)
-            noise_pred[:, :, :condition_count] = 0          # source frames get zero velocity (:736)
-            latents = self.scheduler.step(noise_pred, t, latents, return_dict=False)[0]
-            if callback_on_step_end is not None:
-                kw = {"latents": latents, "prompt_embeds": prompt_embeds, "negative_prompt_embeds": negative_prompt_embeds}
-                outs = callback_on_step_end(self, i, t, {k: kw[k] for k in callback_on_step_end_tensor_inputs})
-                latents = outs.pop("latents", latents)
-                # (:747-748) popped like the reference does; like there, the DiT keeps the embeddings of step 0
-                prompt_embeds = outs.pop("prompt_embeds", prompt_embeds)
-                negative_prompt_embeds = outs.pop("negative_prompt_embeds", negative_prompt_embeds)
+        # The prompt embeddings are fixed from here to the last step (:606; the callback's replacements never reach the
+        # DiT, see below), so the text embedding and the blocks' cross-attention K / V are computed at the first step
+        # only (dit.enable_context_cache); the cache lives for this call alone.
+        scoped_cache = (getattr(self.transformer, "_ctx_cache", 0) is None
+                        and os.environ.get("VCOF_CONTEXT_CACHE", "1") != "0")
+        if scoped_cache:
+            self.transformer.enable_context_cache()
+        try:
+            for i, t in enumerate(timesteps):
+                self.transformer.current_steps = i
+                if self._interrupt:
+                    continue
+                x = torch.cat([latents] * 2) if do_cfg else latents
+                if hasattr(self.scheduler, "scale_model_input"):
+                    x = self.scheduler.scale_model_input(x, t)
+                timestep = t.expand(x.shape[0])
+                fsi = gfi = None
+                if repeat_rope and video is not None:
+                    fsi = [condition_count] * x.shape[0]
+                    if cot:
+                        gfi = [(condition_count, condition_count + ground_latent_count)] * x.shape[0]
+                noise_pred = self.transformer(x=x, context=in_prompt_embeds, t=timestep, seq_len=seq_len,
+                                              frame_split_indices=fsi, ground_frame_indices=gfi)
+                if do_cfg:
+                    uncond, text = noise_pred.chunk(2)
+                    noise_pred = uncond + self.guidance_scale * (text - uncond)
+                noise_pred[:, :, :condition_count] = 0          # source frames get zero velocity (:736)
+                latents = self.scheduler.step(noise_pred, t, latents, return_dict=False)[0]
+                if callback_on_step_end is not None:
+                    kw = {"latents": latents, "prompt_embeds": prompt_embeds,
+                          "negative_prompt_embeds": negative_prompt_embeds}
+                    outs = callback_on_step_end(self, i, t, {k: kw[k] for k in callback_on_step_end_tensor_inputs})
+                    latents = outs.pop("latents", latents)
+                    # (:747-748) popped like the reference does; like there, the DiT keeps the embeddings of step 0
+                    prompt_embeds = outs.pop("prompt_embeds", prompt_embeds)
+                    negative_prompt_embeds = outs.pop("negative_prompt_embeds", negative_prompt_embeds)
+        finally:
+            if scoped_cache:
+                self.transformer.disable_context_cache()
 
         ground_video = edit_video = None
         # any output_type other than "numpy" (or this repo's "uint8") decodes nothing: the reference then hands the INPUT
