@@ -81,6 +81,11 @@ def test_cot_layout_and_kwargs():
     assert tuple(out.edit_videos.shape) == (1, 3, 9, 32, 48)
     assert tuple(out.videos.shape) == (1, 3, 10, 32, 48)
     assert float(out.videos.min()) >= 0.0 and float(out.videos.max()) <= 1.0
+    # one host copy of the clip: the two segments are views of `videos`, in the reference's order (ground first)
+    assert torch.equal(out.videos[:, :, :1], out.ground_videos) and torch.equal(out.videos[:, :, 1:], out.edit_videos)
+    import numpy as np
+    assert np.shares_memory(out.videos.numpy(), out.ground_videos.numpy())
+    assert np.shares_memory(out.videos.numpy(), out.edit_videos.numpy())
 
 
 def test_cfg_batches_two_and_combines():

@@ -187,18 +187,24 @@ class WanPipeline:
         noise = randn_tensor(tuple(org.shape), generator=generator, device=device, dtype=dtype)
         return torch.cat([org, noise], dim=2)
 
-    def decode_latents(self, latents):
-        """:423-428 — decode, map [-1,1] -> [0,1], fp32 numpy on the host.  Same values as the reference's
-        `frames.cpu().float().numpy()` (bf16 -> fp32 is exact wherever it happens); the widening runs on the device
-        instead of element by element on the host (0.4 GB of fp32 for 38 frames of 720p)."""
+    def _decode_device(self, latents):
+        """:423-426 on the device: decode, map [-1,1] -> [0,1] in the VAE's dtype as the reference does, widen to fp32
+        (bf16 -> fp32 is exact wherever it happens; on the device it is not an element-by-element host loop)."""
         frames = self.vae.decode(latents.to(self.vae.dtype)).sample
-        frames = (frames / 2 + 0.5).clamp(0, 1)
-        return frames.float().cpu().numpy()
+        return (frames / 2 + 0.5).clamp(0, 1).float()
+
+    def decode_latents(self, latents):
+        """:423-428 — fp32 numpy [B, 3, T, H, W] in [0,1] on the host; same values as the reference's
+        `frames.cpu().float().numpy()`."""
+        return self._decode_device(latents).cpu().numpy()
+
+    def _decode_frames_device(self, latents):
+        return self.vae.decode_frames(latents.to(self.vae.dtype))
 
     def decode_frames(self, latents):
         """decode_latents + the uint8 conversion of save_videos_grid (utils/utils.py:66) on the device: uint8
         [B, T, H, W, 3] numpy on the host, bit-identical to what the reference writes to the video file."""
-        return self.vae.decode_frames(latents.to(self.vae.dtype)).cpu().numpy()
+        return self._decode_frames_device(latents).cpu().numpy()
 
     # ---- __call__ (:518-799) -----------------------------------------------------------------------------------
     @torch.no_grad()
@@ -301,20 +307,30 @@ class WanPipeline:
         out_video = video
         if output_type in ("numpy", "uint8"):
             # "uint8" (not in the reference): byte frames [B, T, H, W, 3] converted on the device; time is axis 1 there
-            decode, t_axis = (self.decode_latents, 2) if output_type == "numpy" else (self.decode_frames, 1)
+            decode, t_axis = (self._decode_device, 2) if output_type == "numpy" else (self._decode_frames_device, 1)
             if cot:
+                # (:770-777) the ground and the edit segment are decoded separately and concatenated along time.  The
+                # concatenation happens on the device and ONE copy brings the clip to the host (0.4 GB of fp32 for 38
+                # frames of 720p: the reference's two host arrays + np.concatenate move it three times);
+                # `ground_videos` / `edit_videos` are views of `videos`.
                 g0, g1 = condition_count, condition_count + ground_latent_count
                 parts = []
                 if g1 > g0 and g0 < latents.shape[2]:
-                    ground_video = decode(latents[:, :, g0:g1])
-                    parts.append(ground_video)
+                    parts.append(decode(latents[:, :, g0:g1]))
+                n_ground = parts[0].shape[t_axis] if parts else 0
                 if g1 < latents.shape[2]:
-                    edit_video = decode(latents[:, :, g1:])
-                    parts.append(edit_video)
-                out_video = np.concatenate(parts, axis=t_axis)
+                    parts.append(decode(latents[:, :, g1:]))
+                if not parts:
+                    raise ValueError("chain-of-frames latents hold neither a ground nor an edit segment to decode")
+                out_video = (torch.cat(parts, dim=t_axis) if len(parts) > 1 else parts[0]).cpu().numpy()
+                cut = [slice(None)] * t_axis
+                if n_ground:
+                    ground_video = out_video[tuple(cut + [slice(0, n_ground)])]
+                if out_video.shape[t_axis] > n_ground:
+                    edit_video = out_video[tuple(cut + [slice(n_ground, None)])]
             else:
                 if condition_count < latents.shape[2]:
-                    edit_video = decode(latents[:, :, condition_count:])
+                    edit_video = decode(latents[:, :, condition_count:]).cpu().numpy()
                 out_video = edit_video
         self.maybe_free_model_hooks()
         if not return_dict:
