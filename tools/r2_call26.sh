@@ -18,4 +18,4 @@ PY
 timeout 200 $N -k regex:vae_attn -s 2 -c 1 -o gpurun_out/r2c_vae_attn python /tmp/vae_attn_once.py > gpurun_out/r2c26_ncu_vae_attn.log 2>&1
 timeout 300 $N -k regex:conv_lines -s 1 -c 7 -o gpurun_out/r2c_conv_lines python tools/vae_bench.py --frames 9 > gpurun_out/r2c26_ncu_conv.log 2>&1
 ls -la gpurun_out/r2c_* gpurun_out/r2c26_*
-tail -2 gpurun_out/r2c26_ncu_vae_attn.log gpurun_out/r2c26_ncu_conv.log
+tail -n 2 gpurun_out/r2c26_ncu_vae_attn.log gpurun_out/r2c26_ncu_conv.log
