@@ -162,3 +162,40 @@ def test_context_cache_is_scoped_to_the_denoising_loop(monkeypatch):
     run(dit)
     assert dit.seen == [False] * 4 and dit.events == []
     run(StubDiT())                                                       # a DiT without the cache surface: untouched
+
+
+@pytest.mark.parametrize("guidance", [1.0, 5.0])
+def test_pipeline_with_the_real_dit_is_identical_with_and_without_the_context_cache(guidance, monkeypatch):
+    """The whole denoising loop through videocof_b200.dit (libvcof entry points replaced by their contract statements,
+    tests/vcof_emulator.py) with the pipeline's scoped context cache on (default) and off: same videos, bit for bit,
+    with and without classifier-free guidance (batched CFG pair)."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import vcof_emulator
+    from gen_golden import DIT_CASES
+    from oracle.dit_oracle import DiTConfig, make_dit_params
+    from videocof_b200.dit import WanTransformer3DModel
+    vcof_emulator.install_dit(monkeypatch)
+    ckw, _, _, _ = DIT_CASES["dit_tiny"]
+    cfg = DiTConfig(**ckw)
+    dit = WanTransformer3DModel(**cfg.to_kwargs())
+    dit.load_state_dict(make_dit_params(cfg, seed=11), strict=True)
+    dit = dit.to(torch.bfloat16).eval()
+    vae = StubVAE()
+    vae.dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(5)
+    emb, neg = [torch.randn(6, cfg.text_dim, generator=g).bfloat16()], [torch.randn(4, cfg.text_dim, generator=g).bfloat16()]
+
+    def run():
+        pipe = WanPipeline(None, None, vae, dit, FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1))
+        return pipe(video=torch.zeros(1, 3, 5, 16, 16), prompt_embeds=emb, negative_prompt_embeds=neg if guidance > 1 else None,
+                    height=16, width=16, source_frames=5, reasoning_frames=4, num_inference_steps=3,
+                    guidance_scale=guidance, shift=3, repeat_rope=True, cot=True,
+                    generator=torch.Generator().manual_seed(1)).videos
+
+    cached = run()
+    assert dit._ctx_cache is None
+    monkeypatch.setenv("VCOF_CONTEXT_CACHE", "0")
+    plain = run()
+    assert torch.equal(cached, plain) and float(cached.std()) > 0
